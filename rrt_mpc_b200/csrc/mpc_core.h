@@ -1,0 +1,758 @@
+// mpc_core.h — per-problem MPC tracking-step mathematics for libcudampc (sm_100a).
+//
+// One tracking problem = the horizon QP of /root/reference/src/control/mpc_controller.py:47-117
+// (n = 11N+5 variables, m = 19N+7 rows) solved by an OSQP-equivalent ADMM
+// (mpc_controller.py:119-132 settings) plus polish.  Everything here is written as
+// "stage-parallel" routines: routine(k) touches only stage k's record (and reads its neighbours'),
+// so a warp runs them with lanes striding over stages, separated by barriers.  The only sequential
+// parts are the banded LDL' factorisation and the two triangular sweeps ("the chain").
+//
+// The same header compiles for the host (tests/emu, a lane-by-lane emulation used to debug the
+// index logic where no GPU is available).  The product path is the CUDA kernel in cudampc.cu.
+//
+// Formulation notes:
+//  * unscaled problem (OSQP `scaling=0`): A's structural entries stay +-1, bounds stay shared constants;
+//  * merged row state v = z + y/rho for inequality rows (z = clip(v), y = rho (v - z)); equality rows
+//    keep z = b and store y;
+//  * slack columns are eliminated inside the linear solve (they are leaves of the elimination tree),
+//    leaving a banded SPD system of order 6N+4 and half-bandwidth 6 in (X,Y,psi,v,a,delta) stage order;
+//  * polish = the same machinery with per-row weights {0, 1/delta} (reduced form of OSQP's polish KKT).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define MPC_HD __host__ __device__ __forceinline__
+#else
+#define MPC_HD inline
+#endif
+
+namespace mpc {
+
+// ----------------------------------------------------------------------------------------------
+// Parameters / settings as the kernel sees them (filled by the C-ABI from cudampc_params/settings)
+// ----------------------------------------------------------------------------------------------
+struct Params {
+  double L, dt;
+  double q[4], r[2], qn[4];          // diagonals of Q, R, Q_N (objective uses 2*these as P)
+  double u_lo[2], u_hi[2];
+  double v_lo, v_hi;
+  double du_lo[2], du_hi[2];
+  double w_v, w_u, w_du;             // slack weights (P entries are 2*w)
+  int N;
+};
+
+struct Settings {
+  double eps_abs, eps_rel;
+  double rho0, alpha, sigma;
+  double adaptive_rho_tolerance, rho_eq_factor, rho_min, rho_max, delta;
+  int max_iter, check_termination, adaptive_rho, adaptive_rho_interval;
+  int polish_passes, polish_refine_iter, warm_start;
+};
+
+enum { STATUS_SOLVED = 1, STATUS_SOLVED_INACCURATE = 2, STATUS_MAX_ITER = -2, STATUS_UNSOLVED = -10 };
+
+// ----------------------------------------------------------------------------------------------
+// Workspace layout (doubles) of one problem
+// ----------------------------------------------------------------------------------------------
+// stage record (stride SR, odd => conflict-free for lanes striding over stages)
+enum {
+  R_XU = 0,    // X,Y,psi,v,a,delta        (terminal stage: first 4 only)
+  R_S = 6,     // sv, su0, su1, sdu0, sdu1 (terminal: sv only)
+  R_V = 11,    // merged row state, [3*g + r], g: 0 v,1 u0,2 u1,3 du0,4 du1 ; r: 0 hi,1 lo,2 s>=0
+  R_YE = 26,   // duals of the 4 dynamics rows k -> k+1
+  R_LIN = 30,  // a02,a03,a12,a13,b21,c0,c1
+  R_Q = 37,    // linear cost of x_k  (-2 Q ref_k)
+  R_ST = 41,   // s-tilde / reduced slack rhs scratch (5)
+  R_PAD = 46,
+  SR = 47
+};
+enum { H_X0 = 0, H_UPREV = 4, H_YI = 6, H_ACT = 10, HDR_FIXED = 10 };
+
+MPC_HD int hdr_size(int N) { return HDR_FIXED + ((N + 2 + 1) >> 1); }
+MPC_HD int nband(int N) { return 6 * N + 4; }
+MPC_HD int footprint(int N) {
+  int f = hdr_size(N) + (N + 1) * (SR + 7) + 7 * nband(N);
+  return f | 1;  // odd => conflict-free when lanes stride over problems
+}
+// warm-start state kept in HBM between calls: per stage xu(6) s(5) v(15) ye(4), + yi(4) + rho
+MPC_HD int warm_size(int N) { return 30 * (N + 1) + 5; }
+
+struct View {
+  double* base;
+  int N;
+  MPC_HD double* hdr() const { return base; }
+  MPC_HD int* act() const { return reinterpret_cast<int*>(base + H_ACT); }  // [N+1] stage masks + [N+1]=init rows
+  MPC_HD double* rec(int k) const { return base + hdr_size(N) + k * SR; }
+  MPC_HD double* bx(int k) const { return base + hdr_size(N) + (N + 1) * SR + 7 * k; }
+  MPC_HD double* band(int i) const { return base + hdr_size(N) + (N + 1) * (SR + 7) + 7 * i; }
+};
+
+MPC_HD double clipd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+MPC_HD double dmax(double a, double b) { return a > b ? a : b; }
+
+// bounds of soft group g of stage k
+MPC_HD void group_bounds(const Params& p, const double* hdr, int k, int g, double& lo, double& hi) {
+  if (g == 0) { lo = p.v_lo; hi = p.v_hi; }
+  else if (g <= 2) { lo = p.u_lo[g - 1]; hi = p.u_hi[g - 1]; }
+  else {
+    double off = (k == 0) ? hdr[H_UPREV + g - 3] : 0.0;
+    lo = p.du_lo[g - 3] + off; hi = p.du_hi[g - 3] + off;
+  }
+}
+MPC_HD double group_ps(const Params& p, int g) { return 2.0 * (g == 0 ? p.w_v : (g <= 2 ? p.w_u : p.w_du)); }
+MPC_HD int ngroups(int N, int k) { return k < N ? 5 : 1; }
+
+// ----------------------------------------------------------------------------------------------
+// Linear-system mode: ADMM (uniform rho) or polish (activity bits, weights {0,1/delta})
+// ----------------------------------------------------------------------------------------------
+struct Mode {
+  int polish;        // 0: ADMM, 1: polish
+  double rho, rho_eq, reg;   // reg = sigma (ADMM) or delta (polish)
+  double inv_delta;
+};
+MPC_HD Mode admm_mode(double rho, const Settings& s) {
+  Mode m; m.polish = 0; m.rho = rho; m.rho_eq = s.rho_eq_factor * rho; m.reg = s.sigma; m.inv_delta = 0.0; return m;
+}
+MPC_HD Mode polish_mode(const Settings& s) {
+  Mode m; m.polish = 1; m.rho = 0.0; m.rho_eq = 0.0; m.reg = s.delta; m.inv_delta = 1.0 / s.delta; return m;
+}
+
+struct GroupCoef { double kappa, mss_inv, csg; };
+// activity bits of a group: bit0 hi-row, bit1 lo-row, bit2 s>=0 row
+MPC_HD GroupCoef group_coef(const Mode& m, double ps, int bits) {
+  GroupCoef c;
+  if (!m.polish) {
+    c.kappa = 2.0 * m.rho; c.mss_inv = 1.0 / (ps + m.reg + 3.0 * m.rho); c.csg = 0.0;
+  } else {
+    double a1 = (bits & 1) ? 1.0 : 0.0, a2 = (bits & 2) ? 1.0 : 0.0, a3 = (bits & 4) ? 1.0 : 0.0;
+    double d = m.reg;
+    double mssd = (ps + d) * d + (a1 + a2 + a3);          // m_ss * delta
+    c.mss_inv = d / mssd;
+    c.csg = (a2 - a1) * m.inv_delta;
+    c.kappa = ((a1 + a2) * ((ps + d) * d + a3) + 4.0 * a1 * a2) / (d * mssd);   // cancellation-free Schur term
+  }
+  return c;
+}
+MPC_HD double eq_weight(const Mode& m, int active) { return m.polish ? (active ? m.inv_delta : 0.0) : m.rho_eq; }
+
+// ----------------------------------------------------------------------------------------------
+// np.unwrap over the window yaw column (mpc_controller.py:59-60), sequential, lane 0
+// ----------------------------------------------------------------------------------------------
+MPC_HD double np_mod(double a, double b) {
+  double r = fmod(a, b);
+  if (r != 0.0 && ((b < 0.0) != (r < 0.0))) r += b;
+  return r;
+}
+// in: yaw[k] at stride `stride`; out: unwrapped values written to out[k] at stride ostride
+MPC_HD void unwrap_yaw(const double* yaw, int stride, int count, double* out, int ostride) {
+  const double PI = 3.141592653589793;
+  double cum = 0.0, prev = yaw[0];
+  out[0] = prev;
+  for (int k = 1; k < count; ++k) {
+    double cur = yaw[(size_t)k * stride];
+    double dd = cur - prev;
+    double ddmod = np_mod(dd + PI, 2.0 * PI) - PI;
+    if (ddmod == -PI && dd > 0.0) ddmod = PI;
+    double corr = ddmod - dd;
+    if (fabs(dd) < PI) corr = 0.0;
+    cum += corr;
+    out[(size_t)k * ostride] = cur + cum;
+    prev = cur;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Linearisation of stage k (vehicle_model.py:24-45 as called from mpc_controller.py:65-70,108-109)
+//   linearised at the unwrapped reference row max(k-1,0), ulin = 0.
+//   lin7 = {a02,a03,a12,a13,b21,c0,c1};  A[2][3] = dt/L*tan(0) = 0, c2 = c3 = 0 exactly.
+// ----------------------------------------------------------------------------------------------
+MPC_HD void linearize_point(const Params& p, double X, double Y, double yaw, double v, double* lin7) {
+  double c = cos(yaw), s = sin(yaw);
+  double sec2 = 1.0 / (1.0 * 1.0 + 1e-9);            // cos(0)^2 + 1e-9  (vehicle_model.py:31)
+  double a02 = -p.dt * v * s, a03 = p.dt * c, a12 = p.dt * v * c, a13 = p.dt * s;
+  double b21 = p.dt * (v / p.L) * sec2;
+  double fx0 = X + p.dt * v * cos(yaw + 0.0), fx1 = Y + p.dt * v * sin(yaw + 0.0);
+  // c_aff = fx - A @ xlin  (row dot in index order, zeros included as exact no-ops)
+  double ax0 = X + a02 * yaw + a03 * v;
+  double ax1 = Y + a12 * yaw + a13 * v;
+  lin7[0] = a02; lin7[1] = a03; lin7[2] = a12; lin7[3] = a13; lin7[4] = b21;
+  lin7[5] = fx0 - ax0; lin7[6] = fx1 - ax1;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Row-value providers.  A "row provider" RP answers, for the rows owned by stage k:
+//   dyn(k, r)  r=0..3   value attached to dynamics row r of stage k (k < N)
+//   init(r)             value attached to the X_0 = x0 rows
+//   grp(k, g)           the pair-combined value for the (x,u) part of soft group g of stage k
+// gather_xu() forms  sum_i A_ij * value_i  for the six (x,u) unknowns of stage k.
+// ----------------------------------------------------------------------------------------------
+template <class RP>
+MPC_HD void gather_xu(const View& w, const Params& p, int k, const RP& rp, double* out) {
+  const int N = w.N;
+  for (int j = 0; j < 6; ++j) out[j] = 0.0;
+  if (k >= 1) { for (int j = 0; j < 4; ++j) out[j] += rp.dyn(k - 1, j); }
+  else { for (int j = 0; j < 4; ++j) out[j] += rp.init(j); }
+  out[3] += rp.grp(k, 0);
+  if (k < N) {
+    const double* lin = w.rec(k) + R_LIN;
+    double d0 = rp.dyn(k, 0), d1 = rp.dyn(k, 1), d2 = rp.dyn(k, 2), d3 = rp.dyn(k, 3);
+    out[0] -= d0;
+    out[1] -= d1;
+    out[2] -= lin[0] * d0 + lin[2] * d1 + d2;
+    out[3] -= lin[1] * d0 + lin[3] * d1 + d3;
+    out[4] -= p.dt * d3;
+    out[5] -= lin[4] * d2;
+    for (int i = 0; i < 2; ++i) {
+      out[4 + i] += rp.grp(k, 1 + i) + rp.grp(k, 3 + i);
+      if (k + 1 < N) out[4 + i] -= rp.grp(k + 1, 3 + i);
+    }
+  }
+}
+
+// (A x) for the dynamics rows of stage k from a vector accessor XV(k', j)
+template <class XV>
+MPC_HD void dyn_rows(const View& w, const Params& p, int k, const XV& xv, double* z) {
+  const double* lin = w.rec(k) + R_LIN;
+  double X = xv(k, 0), Y = xv(k, 1), ps = xv(k, 2), v = xv(k, 3), a = xv(k, 4), d = xv(k, 5);
+  z[0] = xv(k + 1, 0) - (X + lin[0] * ps + lin[1] * v);
+  z[1] = xv(k + 1, 1) - (Y + lin[2] * ps + lin[3] * v);
+  z[2] = xv(k + 1, 2) - (ps + lin[4] * d);
+  z[3] = xv(k + 1, 3) - (v + p.dt * a);
+}
+// g value of soft group g of stage k
+template <class XV>
+MPC_HD double group_g(int k, int g, const XV& xv) {
+  if (g == 0) return xv(k, 3);
+  if (g <= 2) return xv(k, 4 + g - 1);
+  double cur = xv(k, 4 + g - 3);
+  return k > 0 ? cur - xv(k - 1, 4 + g - 3) : cur;
+}
+
+struct StateXV { View w; MPC_HD double operator()(int k, int j) const { return w.rec(k)[R_XU + j]; } };
+struct BxXV { View w; MPC_HD double operator()(int k, int j) const { return w.bx(k)[j]; } };
+
+// ----------------------------------------------------------------------------------------------
+// Problem setup
+// ----------------------------------------------------------------------------------------------
+// stage k: linearise + cost vector from the (already unwrapped, stored in R_Q slots temporarily? no:)
+// ref rows are read from global memory `ref` ([N+1][4], yaw replaced by unwrapped yaw in `uyaw`).
+MPC_HD void setup_stage(const View& w, const Params& p, int k, const double* ref, const double* uyaw) {
+  const int N = w.N;
+  double* rc = w.rec(k);
+  if (k < N) {
+    int kl = k > 0 ? k - 1 : 0;
+    linearize_point(p, ref[4 * kl + 0], ref[4 * kl + 1], uyaw[kl], ref[4 * kl + 3], rc + R_LIN);
+  } else {
+    for (int j = 0; j < 7; ++j) rc[R_LIN + j] = 0.0;
+  }
+  const double* qd = k < N ? p.q : p.qn;
+  rc[R_Q + 0] = -2.0 * qd[0] * ref[4 * k + 0];
+  rc[R_Q + 1] = -2.0 * qd[1] * ref[4 * k + 1];
+  rc[R_Q + 2] = -2.0 * qd[2] * uyaw[k];
+  rc[R_Q + 3] = -2.0 * qd[3] * ref[4 * k + 3];
+}
+
+// cold start: x = 0, y = 0, z = clip(0, l, u)  (v = z for inequality rows)
+MPC_HD void cold_start_stage(const View& w, const Params& p, int k) {
+  double* rc = w.rec(k);
+  for (int j = 0; j < 11; ++j) rc[R_XU + j] = 0.0;
+  for (int g = 0; g < 5; ++g) {
+    double lo = 0.0, hi = 0.0;
+    if (g < ngroups(w.N, k)) group_bounds(p, w.hdr(), k, g, lo, hi);
+    rc[R_V + 3 * g + 0] = fmin(0.0, hi);
+    rc[R_V + 3 * g + 1] = fmax(0.0, lo);
+    rc[R_V + 3 * g + 2] = 0.0;
+  }
+  for (int r = 0; r < 4; ++r) rc[R_YE + r] = 0.0;
+  for (int j = 0; j < 5; ++j) rc[R_ST + j] = 0.0;
+  if (k == 0) for (int r = 0; r < 4; ++r) w.hdr()[H_YI + r] = 0.0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Band assembly: rows 6k..6k+5 of  M = P + reg I + sum_rows w_i a_i a_i' + sum_groups kappa g g'
+//   band(i)[d-1] = M[i][i-d], d = 1..6 ; band(i)[6] = M[i][i]
+// ----------------------------------------------------------------------------------------------
+MPC_HD int act_group_bits(const View& w, int k, int g) { return (w.act()[k] >> (3 * g)) & 7; }
+MPC_HD int act_dyn_bit(const View& w, int k, int r) { return (w.act()[k] >> (15 + r)) & 1; }
+MPC_HD int act_init_bit(const View& w, int r) { return (w.act()[w.N + 1] >> r) & 1; }
+
+MPC_HD void assemble_stage(const View& w, const Params& p, const Mode& m, int k) {
+  const int N = w.N;
+  const int nj = k < N ? 6 : 4;
+  double D[6][6], E[6][6];   // D: diagonal block (lower part used); E: coupling to stage k-1 (rows k, cols k-1)
+  for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) { D[a][b] = 0.0; E[a][b] = 0.0; }
+  const double* qd = k < N ? p.q : p.qn;
+  for (int j = 0; j < 4; ++j) D[j][j] = 2.0 * qd[j] + m.reg;
+  if (k < N) { D[4][4] = 2.0 * p.r[0] + m.reg; D[5][5] = 2.0 * p.r[1] + m.reg; }
+  // rows arriving at x_k: init rows (k == 0) or dynamics rows of stage k-1
+  if (k == 0) {
+    for (int r = 0; r < 4; ++r) D[r][r] += eq_weight(m, m.polish ? act_init_bit(w, r) : 1);
+  } else {
+    const double* lin = w.rec(k - 1) + R_LIN;
+    double om[4];
+    for (int r = 0; r < 4; ++r) om[r] = eq_weight(m, m.polish ? act_dyn_bit(w, k - 1, r) : 1);
+    // row r of stage k-1: +1 at x_k[r], -(A,B) part on stage k-1
+    for (int r = 0; r < 4; ++r) D[r][r] += om[r];
+    // E[r][:] = om[r] * a_r^{(k-1)}
+    E[0][0] = -om[0]; E[0][2] = -om[0] * lin[0]; E[0][3] = -om[0] * lin[1];
+    E[1][1] = -om[1]; E[1][2] = -om[1] * lin[2]; E[1][3] = -om[1] * lin[3];
+    E[2][2] = -om[2]; E[2][5] = -om[2] * lin[4];
+    E[3][3] = -om[3]; E[3][4] = -om[3] * p.dt;
+  }
+  if (k < N) {
+    const double* lin = w.rec(k) + R_LIN;
+    double om[4];
+    for (int r = 0; r < 4; ++r) om[r] = eq_weight(m, m.polish ? act_dyn_bit(w, k, r) : 1);
+    // a_0 = (-1,0,-a02,-a03,0,0), a_1 = (0,-1,-a12,-a13,0,0), a_2 = (0,0,-1,0,0,-b21), a_3 = (0,0,0,-1,-dt,0)
+    double a0[6] = {-1.0, 0.0, -lin[0], -lin[1], 0.0, 0.0};
+    double a1[6] = {0.0, -1.0, -lin[2], -lin[3], 0.0, 0.0};
+    double a2[6] = {0.0, 0.0, -1.0, 0.0, 0.0, -lin[4]};
+    double a3[6] = {0.0, 0.0, 0.0, -1.0, -p.dt, 0.0};
+    for (int a = 0; a < 6; ++a)
+      for (int b = 0; b <= a; ++b)
+        D[a][b] += om[0] * a0[a] * a0[b] + om[1] * a1[a] * a1[b] + om[2] * a2[a] * a2[b] + om[3] * a3[a] * a3[b];
+  }
+  // soft groups
+  {
+    GroupCoef c = group_coef(m, group_ps(p, 0), m.polish ? act_group_bits(w, k, 0) : 0);
+    D[3][3] += c.kappa;
+  }
+  if (k < N) {
+    for (int i = 0; i < 2; ++i) {
+      GroupCoef cu = group_coef(m, group_ps(p, 1 + i), m.polish ? act_group_bits(w, k, 1 + i) : 0);
+      GroupCoef cd = group_coef(m, group_ps(p, 3 + i), m.polish ? act_group_bits(w, k, 3 + i) : 0);
+      D[4 + i][4 + i] += cu.kappa + cd.kappa;
+      if (k > 0) E[4 + i][4 + i] -= cd.kappa;                 // (u_k - u_{k-1}) coupling
+      if (k + 1 < N) {
+        GroupCoef cn = group_coef(m, group_ps(p, 3 + i), m.polish ? act_group_bits(w, k + 1, 3 + i) : 0);
+        D[4 + i][4 + i] += cn.kappa;
+      }
+    }
+  }
+  for (int j = 0; j < nj; ++j) {
+    double* b = w.band(6 * k + j);
+    for (int d = 1; d <= 6; ++d) {
+      double val;
+      if (d <= j) val = D[j][j - d];
+      else val = (k > 0) ? E[j][j + 6 - d] : 0.0;
+      b[d - 1] = val;
+    }
+    b[6] = D[j][j];
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Banded LDL' (unit lower L, half-bandwidth 6), in place, sequential.
+//   after: band(i)[d-1] = L[i][i-d], band(i)[6] = 1/D[i]
+// ----------------------------------------------------------------------------------------------
+MPC_HD void factor_band(const View& w) {
+  const int n = nband(w.N);
+  for (int i = 0; i < n; ++i) {
+    double* bi = w.band(i);
+    double W[6];                       // W[d-1] = L[i][i-d] * D[i-d]
+    double dii = bi[6];
+    const int dmax_ = i < 6 ? i : 6;
+    for (int d = dmax_; d >= 1; --d) {  // column j = i-d, increasing j
+      const int j = i - d;
+      const double* bj = w.band(j);
+      double s = bi[d - 1];
+      // sum over t = max(i-6, j-6, 0) .. j-1 : W_i[t] * L[j][t] ;  t = i - e, e = d+1..dmax_ ; L[j][t] = bj[(j-t)-1] = bj[e-d-1]
+      for (int e = d + 1; e <= dmax_; ++e) {
+        if (e - d <= 6) s -= W[e - 1] * bj[e - d - 1];
+      }
+      W[d - 1] = s;
+      double lij = s * bj[6];          // bj[6] already holds 1/D[j]
+      bi[d - 1] = lij;
+      dii -= s * lij;
+    }
+    for (int d = dmax_ + 1; d <= 6; ++d) bi[d - 1] = 0.0;
+    bi[6] = 1.0 / dii;
+  }
+}
+
+// Solve L D L' x = b in place on bx (stride 7 per stage), sequential.
+MPC_HD void chain_solve(const View& w) {
+  const int N = w.N;
+  const int n = nband(N);
+  // forward: w_i = b_i - sum_d L[i][i-d] w_{i-d}; then scale by 1/D
+  double h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, h5 = 0;   // h{d-1} = w_{i-d}
+  {
+    int i = 0;
+    for (int k = 0; k <= N; ++k) {
+      double* b = w.bx(k);
+      const int nj = k < N ? 6 : 4;
+      for (int j = 0; j < nj; ++j, ++i) {
+        const double* l = w.band(i);
+        double acc = b[j];
+        acc = fma(-l[5], h5, acc); acc = fma(-l[4], h4, acc); acc = fma(-l[3], h3, acc);
+        acc = fma(-l[2], h2, acc); acc = fma(-l[1], h1, acc); acc = fma(-l[0], h0, acc);
+        b[j] = acc * l[6];
+        h5 = h4; h4 = h3; h3 = h2; h2 = h1; h1 = h0; h0 = acc;
+      }
+    }
+  }
+  // backward: x_i = w_i - sum_d L[i+d][i] x_{i+d}
+  h0 = h1 = h2 = h3 = h4 = h5 = 0;                           // h{d-1} = x_{i+d}
+  {
+    int i = n - 1;
+    for (int k = N; k >= 0; --k) {
+      double* b = w.bx(k);
+      const int nj = k < N ? 6 : 4;
+      for (int j = nj - 1; j >= 0; --j, --i) {
+        double acc = b[j];
+        // L[i+d][i] = band(i+d)[d-1]; rows beyond n-1 contribute 0 (h = 0)
+        const double* l = w.band(i);
+        double c5 = (i + 6 < n) ? l[7 * 6 + 5] : 0.0;
+        double c4 = (i + 5 < n) ? l[7 * 5 + 4] : 0.0;
+        double c3 = (i + 4 < n) ? l[7 * 4 + 3] : 0.0;
+        double c2 = (i + 3 < n) ? l[7 * 3 + 2] : 0.0;
+        double c1 = (i + 2 < n) ? l[7 * 2 + 1] : 0.0;
+        double c0 = (i + 1 < n) ? l[7 * 1 + 0] : 0.0;
+        acc = fma(-c5, h5, acc); acc = fma(-c4, h4, acc); acc = fma(-c3, h3, acc);
+        acc = fma(-c2, h2, acc); acc = fma(-c1, h1, acc); acc = fma(-c0, h0, acc);
+        b[j] = acc;
+        h5 = h4; h4 = h3; h3 = h2; h2 = h1; h1 = h0; h0 = acc;
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// ADMM step, split in two stage-parallel halves
+//   A1(k): consume x-tilde (bx) and s-tilde (R_ST): relax x, update row states (v, ye, yi)
+//   A2(k): from the new state form t = rho z - y per row, s-tilde, and the banded rhs -> bx
+// ----------------------------------------------------------------------------------------------
+MPC_HD void admm_update_stage(const View& w, const Params& p, const Settings& s, double rho, int k) {
+  const int N = w.N;
+  double* rc = w.rec(k);
+  const double alpha = s.alpha, oma = 1.0 - s.alpha;
+  const double rho_eq = s.rho_eq_factor * rho;
+  BxXV xt{w};
+  // soft groups
+  const int ng = ngroups(N, k);
+  for (int g = 0; g < ng; ++g) {
+    double lo, hi; group_bounds(p, w.hdr(), k, g, lo, hi);
+    double gt = group_g(k, g, xt);
+    double st = rc[R_ST + g];
+    double zt[3] = {gt - st, gt + st, st};
+    double blo[3] = {-1e30, lo, 0.0}, bhi[3] = {hi, 1e30, 1e30};
+    for (int r = 0; r < 3; ++r) {
+      double v = rc[R_V + 3 * g + r];
+      double z = clipd(v, blo[r], bhi[r]);
+      double wv = alpha * zt[r] + oma * z;
+      rc[R_V + 3 * g + r] = wv + (v - z);
+    }
+    rc[R_S + g] = alpha * st + oma * rc[R_S + g];
+  }
+  // equality rows
+  if (k < N) {
+    double zt[4]; dyn_rows(w, p, k, xt, zt);
+    const double* lin = rc + R_LIN;
+    double b[4] = {lin[5], lin[6], 0.0, 0.0};
+    for (int r = 0; r < 4; ++r) rc[R_YE + r] += rho_eq * alpha * (zt[r] - b[r]);
+  }
+  if (k == 0) {
+    double* h = w.hdr();
+    for (int r = 0; r < 4; ++r) h[H_YI + r] += rho_eq * alpha * (xt(0, r) - h[H_X0 + r]);
+  }
+}
+// second half of A1: relax x (kept separate because A1 reads neighbours' x-tilde from bx, not state)
+MPC_HD void admm_relax_x_stage(const View& w, const Settings& s, int k) {
+  double* rc = w.rec(k);
+  const double* b = w.bx(k);
+  const int nj = k < w.N ? 6 : 4;
+  for (int j = 0; j < nj; ++j) rc[R_XU + j] = s.alpha * b[j] + (1.0 - s.alpha) * rc[R_XU + j];
+}
+
+// row provider for the ADMM rhs: value = rho_i z_i - y_i
+struct AdmmRP {
+  View w; const Params* p; double rho, rho_eq;
+  MPC_HD double dyn(int k, int r) const {
+    const double* rc = w.rec(k);
+    double b = r == 0 ? rc[R_LIN + 5] : (r == 1 ? rc[R_LIN + 6] : 0.0);
+    return rho_eq * b - rc[R_YE + r];
+  }
+  MPC_HD double init(int r) const { return rho_eq * w.hdr()[H_X0 + r] - w.hdr()[H_YI + r]; }
+  MPC_HD double t_row(int k, int g, int r) const {
+    double lo, hi; group_bounds(*p, w.hdr(), k, g, lo, hi);
+    double v = w.rec(k)[R_V + 3 * g + r];
+    double z = r == 0 ? fmin(v, hi) : (r == 1 ? fmax(v, lo) : fmax(v, 0.0));
+    return rho * (2.0 * z - v);
+  }
+  MPC_HD double grp(int k, int g) const { return t_row(k, g, 0) + t_row(k, g, 1); }
+};
+
+MPC_HD void admm_rhs_stage(const View& w, const Params& p, const Settings& s, double rho, int k) {
+  const int N = w.N;
+  double* rc = w.rec(k);
+  AdmmRP rp{w, &p, rho, s.rho_eq_factor * rho};
+  const int ng = ngroups(N, k);
+  for (int g = 0; g < ng; ++g) {
+    double t1 = rp.t_row(k, g, 0), t2 = rp.t_row(k, g, 1), t3 = rp.t_row(k, g, 2);
+    double mss_inv = 1.0 / (group_ps(p, g) + s.sigma + 3.0 * rho);
+    rc[R_ST + g] = (s.sigma * rc[R_S + g] + (-t1 + t2 + t3)) * mss_inv;
+  }
+  double out[6];
+  gather_xu(w, p, k, rp, out);
+  double* b = w.bx(k);
+  const int nj = k < N ? 6 : 4;
+  for (int j = 0; j < nj; ++j) {
+    double qj = j < 4 ? rc[R_Q + j] : 0.0;
+    b[j] = s.sigma * rc[R_XU + j] - qj + out[j];
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Residuals of the current iterate (x, z = clip(v), y): per-stage partial maxima
+//   r[0] |Ax - z|, r[1] |Ax|, r[2] |z|, r[3] |Px + q + A'y|, r[4] |Px|, r[5] |A'y|, r[6] |q|
+// mode 0: ADMM state (R_V holds v);  mode 1: polished state (R_V holds y, z := clip(Ax))
+// ----------------------------------------------------------------------------------------------
+struct DualRP {       // value = y_i
+  View w; const Params* p; double rho; int ymode;
+  MPC_HD double dyn(int k, int r) const { return w.rec(k)[R_YE + r]; }
+  MPC_HD double init(int r) const { return w.hdr()[H_YI + r]; }
+  MPC_HD double y_row(int k, int g, int r) const {
+    double v = w.rec(k)[R_V + 3 * g + r];
+    if (ymode) return v;
+    double lo, hi; group_bounds(*p, w.hdr(), k, g, lo, hi);
+    double z = r == 0 ? fmin(v, hi) : (r == 1 ? fmax(v, lo) : fmax(v, 0.0));
+    return rho * (v - z);
+  }
+  MPC_HD double grp(int k, int g) const { return y_row(k, g, 0) + y_row(k, g, 1); }
+};
+
+MPC_HD void residual_stage(const View& w, const Params& p, double rho, int ymode, int k, double* r) {
+  const int N = w.N;
+  const double* rc = w.rec(k);
+  StateXV xs{w};
+  DualRP rp{w, &p, rho, ymode};
+  const int ng = ngroups(N, k);
+  // primal
+  for (int g = 0; g < ng; ++g) {
+    double lo, hi; group_bounds(p, w.hdr(), k, g, lo, hi);
+    double gv = group_g(k, g, xs), sv = rc[R_S + g];
+    double ax[3] = {gv - sv, gv + sv, sv};
+    double blo[3] = {-1e30, lo, 0.0}, bhi[3] = {hi, 1e30, 1e30};
+    for (int q = 0; q < 3; ++q) {
+      double z = ymode ? clipd(ax[q], blo[q], bhi[q]) : clipd(rc[R_V + 3 * g + q], blo[q], bhi[q]);
+      r[0] = dmax(r[0], fabs(ax[q] - z)); r[1] = dmax(r[1], fabs(ax[q])); r[2] = dmax(r[2], fabs(z));
+    }
+  }
+  if (k < N) {
+    double ax[4]; dyn_rows(w, p, k, xs, ax);
+    double b[4] = {rc[R_LIN + 5], rc[R_LIN + 6], 0.0, 0.0};
+    for (int q = 0; q < 4; ++q) {
+      r[0] = dmax(r[0], fabs(ax[q] - b[q])); r[1] = dmax(r[1], fabs(ax[q])); r[2] = dmax(r[2], fabs(b[q]));
+    }
+  }
+  if (k == 0) {
+    const double* h = w.hdr();
+    for (int q = 0; q < 4; ++q) {
+      double ax = xs(0, q), b = h[H_X0 + q];
+      r[0] = dmax(r[0], fabs(ax - b)); r[1] = dmax(r[1], fabs(ax)); r[2] = dmax(r[2], fabs(b));
+    }
+  }
+  // dual
+  double aty[6]; gather_xu(w, p, k, rp, aty);
+  const double* qd = k < N ? p.q : p.qn;
+  const int nj = k < N ? 6 : 4;
+  for (int j = 0; j < nj; ++j) {
+    double pd = j < 4 ? 2.0 * qd[j] : 2.0 * p.r[j - 4];
+    double px = pd * rc[R_XU + j];
+    double qj = j < 4 ? rc[R_Q + j] : 0.0;
+    r[3] = dmax(r[3], fabs(px + qj + aty[j])); r[4] = dmax(r[4], fabs(px)); r[5] = dmax(r[5], fabs(aty[j]));
+    r[6] = dmax(r[6], fabs(qj));
+  }
+  for (int g = 0; g < ng; ++g) {
+    double px = group_ps(p, g) * rc[R_S + g];
+    double ay = -rp.y_row(k, g, 0) + rp.y_row(k, g, 1) + rp.y_row(k, g, 2);
+    r[3] = dmax(r[3], fabs(px + ay)); r[4] = dmax(r[4], fabs(px)); r[5] = dmax(r[5], fabs(ay));
+  }
+}
+
+// rho change: keep (z, y) fixed, re-express v = z + y / rho_new
+MPC_HD void rescale_v_stage(const View& w, const Params& p, double rho_old, double rho_new, int k) {
+  double* rc = w.rec(k);
+  const int ng = ngroups(w.N, k);
+  const double f = rho_old / rho_new;
+  for (int g = 0; g < ng; ++g) {
+    double lo, hi; group_bounds(p, w.hdr(), k, g, lo, hi);
+    double blo[3] = {-1e30, lo, 0.0}, bhi[3] = {hi, 1e30, 1e30};
+    for (int r = 0; r < 3; ++r) {
+      double v = rc[R_V + 3 * g + r];
+      double z = clipd(v, blo[r], bhi[r]);
+      rc[R_V + 3 * g + r] = z + (v - z) * f;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Polish
+// ----------------------------------------------------------------------------------------------
+// pass 1 (from_admm = 1): activity from the ADMM pair (z, y): upper-active  u - z < y  <=> v > hi, etc.;
+//                         then R_V is overwritten by y (inactive rows: exactly 0).
+// later passes:           activity from  Ax + y  (primal-dual active set), y kept only on active rows.
+// returns 1 if the activity mask of this stage changed.
+MPC_HD int polish_activity_stage(const View& w, const Params& p, double rho, int from_admm, int k) {
+  const int N = w.N;
+  double* rc = w.rec(k);
+  StateXV xs{w};
+  int bits = 0;
+  const int ng = ngroups(N, k);
+  for (int g = 0; g < ng; ++g) {
+    double lo, hi; group_bounds(p, w.hdr(), k, g, lo, hi);
+    double blo[3] = {-1e30, lo, 0.0}, bhi[3] = {hi, 1e30, 1e30};
+    double gv = group_g(k, g, xs), sv = rc[R_S + g];
+    double ax[3] = {gv - sv, gv + sv, sv};
+    for (int r = 0; r < 3; ++r) {
+      double v = rc[R_V + 3 * g + r];
+      double y;
+      int a;
+      if (from_admm) {
+        double z = clipd(v, blo[r], bhi[r]);
+        y = rho * (v - z);
+        a = (r == 0) ? (bhi[r] - z < y) : (z - blo[r] < -y);
+      } else {
+        y = v;
+        a = (r == 0) ? (bhi[r] - ax[r] < y) : (ax[r] - blo[r] < -y);
+      }
+      rc[R_V + 3 * g + r] = a ? y : 0.0;
+      bits |= a << (3 * g + r);
+    }
+  }
+  if (k < N) for (int r = 0; r < 4; ++r) { int a = rc[R_YE + r] != 0.0; bits |= a << (15 + r); }
+  int changed = (w.act()[k] != bits) || from_admm;
+  w.act()[k] = bits;
+  if (k == 0) {
+    int ib = 0;
+    for (int r = 0; r < 4; ++r) ib |= (w.hdr()[H_YI + r] != 0.0) << r;
+    changed |= (w.act()[N + 1] != ib);
+    w.act()[N + 1] = ib;
+  }
+  return changed;
+}
+
+// row provider for the polish step: value_i = act_i * (e2_i / delta - y_i),  e2_i = b_i - (A x)_i
+struct PolishRP {
+  View w; const Params* p; double inv_delta; int zero_sol;   // zero_sol: first step, sol = 0 (state not yet reset)
+  MPC_HD double dyn(int k, int r) const {
+    if (!act_dyn_bit(w, k, r)) return 0.0;
+    const double* rc = w.rec(k);
+    double b = r == 0 ? rc[R_LIN + 5] : (r == 1 ? rc[R_LIN + 6] : 0.0);
+    double z[4]; StateXV xs{w}; dyn_rows(w, *p, k, xs, z);
+    return (b - z[r]) * inv_delta - rc[R_YE + r];
+  }
+  MPC_HD double init(int r) const {
+    if (!act_init_bit(w, r)) return 0.0;
+    const double* h = w.hdr();
+    return (h[H_X0 + r] - w.rec(0)[R_XU + r]) * inv_delta - h[H_YI + r];
+  }
+  MPC_HD double row(int k, int g, int r) const {
+    if (!((act_group_bits(w, k, g) >> r) & 1)) return 0.0;
+    double lo, hi; group_bounds(*p, w.hdr(), k, g, lo, hi);
+    StateXV xs{w};
+    const double* rc = w.rec(k);
+    double gv = group_g(k, g, xs), sv = rc[R_S + g];
+    double ax = r == 0 ? gv - sv : (r == 1 ? gv + sv : sv);
+    double b = r == 0 ? hi : (r == 1 ? lo : 0.0);
+    return (b - ax) * inv_delta - rc[R_V + 3 * g + r];
+  }
+  // reduced slack rhs and pair-combined value after eliminating the slack
+  MPC_HD void group_vals(int k, int g, const Mode& m, double& rr_s, double& gval) const {
+    double v1 = row(k, g, 0), v2 = row(k, g, 1), v3 = row(k, g, 2);
+    double ps = group_ps(*p, g);
+    GroupCoef c = group_coef(m, ps, act_group_bits(w, k, g));
+    rr_s = -ps * w.rec(k)[R_S + g] + (-v1 + v2 + v3);
+    gval = v1 + v2 - c.csg * c.mss_inv * rr_s;
+  }
+  Mode mode;
+  MPC_HD double grp(int k, int g) const { double a, b; group_vals(k, g, mode, a, b); return b; }
+};
+
+// S1(k): residual of the un-regularised polish KKT at the current (x, y) folded into the banded rhs
+MPC_HD void polish_rhs_stage(const View& w, const Params& p, const Mode& m, int k) {
+  const int N = w.N;
+  double* rc = w.rec(k);
+  PolishRP rp{w, &p, m.inv_delta, 0, m};
+  const int ng = ngroups(N, k);
+  for (int g = 0; g < ng; ++g) {
+    double rr_s, gval; rp.group_vals(k, g, m, rr_s, gval);
+    rc[R_ST + g] = rr_s;
+  }
+  double out[6];
+  gather_xu(w, p, k, rp, out);
+  double* b = w.bx(k);
+  const double* qd = k < N ? p.q : p.qn;
+  const int nj = k < N ? 6 : 4;
+  for (int j = 0; j < nj; ++j) {
+    double pd = j < 4 ? 2.0 * qd[j] : 2.0 * p.r[j - 4];
+    double qj = j < 4 ? rc[R_Q + j] : 0.0;
+    b[j] = -qj - pd * rc[R_XU + j] + out[j];
+  }
+}
+// S3a(k): ds and dy from the banded correction; y += dy (row-owned); ds left in R_ST
+MPC_HD void polish_dual_stage(const View& w, const Params& p, const Mode& m, int k) {
+  const int N = w.N;
+  double* rc = w.rec(k);
+  BxXV dx{w};
+  StateXV xs{w};
+  const int ng = ngroups(N, k);
+  for (int g = 0; g < ng; ++g) {
+    double lo, hi; group_bounds(p, w.hdr(), k, g, lo, hi);
+    int bits = act_group_bits(w, k, g);
+    GroupCoef c = group_coef(m, group_ps(p, g), bits);
+    double gd = group_g(k, g, dx);
+    double ds = (rc[R_ST + g] - c.csg * gd) * c.mss_inv;
+    rc[R_ST + g] = ds;
+    double gv = group_g(k, g, xs), sv = rc[R_S + g];
+    double ax[3] = {gv - sv, gv + sv, sv};
+    double ad[3] = {gd - ds, gd + ds, ds};
+    double b[3] = {hi, lo, 0.0};
+    for (int r = 0; r < 3; ++r)
+      if ((bits >> r) & 1) rc[R_V + 3 * g + r] += m.inv_delta * (ad[r] - (b[r] - ax[r]));
+  }
+  if (k < N) {
+    double ax[4], ad[4]; dyn_rows(w, p, k, xs, ax); dyn_rows(w, p, k, dx, ad);
+    double b[4] = {rc[R_LIN + 5], rc[R_LIN + 6], 0.0, 0.0};
+    // dyn_rows on the correction has no affine part: ad is linear in dx by construction
+    for (int r = 0; r < 4; ++r)
+      if (act_dyn_bit(w, k, r)) rc[R_YE + r] += m.inv_delta * (ad[r] - (b[r] - ax[r]));
+  }
+  if (k == 0) {
+    double* h = w.hdr();
+    for (int r = 0; r < 4; ++r)
+      if (act_init_bit(w, r)) h[H_YI + r] += m.inv_delta * (dx(0, r) - (h[H_X0 + r] - xs(0, r)));
+  }
+}
+// S3b(k): x += dx, s += ds
+MPC_HD void polish_primal_stage(const View& w, int k) {
+  double* rc = w.rec(k);
+  const double* b = w.bx(k);
+  const int nj = k < w.N ? 6 : 4;
+  for (int j = 0; j < nj; ++j) rc[R_XU + j] += b[j];
+  const int ng = ngroups(w.N, k);
+  for (int g = 0; g < ng; ++g) rc[R_S + g] += rc[R_ST + g];
+}
+// zero the primal/dual solution before the first polish step (sol = 0); activity masks are kept
+MPC_HD void polish_zero_stage(const View& w, int k) {
+  double* rc = w.rec(k);
+  for (int j = 0; j < 11; ++j) rc[R_XU + j] = 0.0;
+  for (int j = 0; j < 15; ++j) rc[R_V + j] = 0.0;
+  for (int r = 0; r < 4; ++r) rc[R_YE + r] = 0.0;
+  if (k == 0) for (int r = 0; r < 4; ++r) w.hdr()[H_YI + r] = 0.0;
+}
+
+// save / restore the iterate of one stage to the HBM warm-start slot ([stage][30] + tail)
+MPC_HD void save_stage(const View& w, int k, double* g) {
+  const double* rc = w.rec(k);
+  double* o = g + 30 * k;
+  for (int j = 0; j < 30; ++j) o[j] = rc[R_XU + j];
+}
+MPC_HD void load_stage(const View& w, int k, const double* g) {
+  double* rc = w.rec(k);
+  const double* o = g + 30 * k;
+  for (int j = 0; j < 30; ++j) rc[R_XU + j] = o[j];
+}
+
+}  // namespace mpc

@@ -1,0 +1,173 @@
+// mpc_solve.h — per-problem driver of the MPC tracking step (OSQP-equivalent ADMM + polish),
+// templated on an execution policy `Exec` that says how stage-parallel phases, reductions and the
+// sequential chain operations are run (CUDA warp in cudampc.cu; lane emulation in tests/emu).
+//
+// Follows /root/reference/src/control/mpc_controller.py:39-141 (what is solved, what is returned)
+// with the solver restated from the published OSQP algorithm (see oracle/ for the CPU statement).
+#pragma once
+#include "mpc_core.h"
+
+namespace mpc {
+
+struct ProblemIO {
+  const double* x0;      // [4]
+  const double* ref;     // [N+1][4] time-major (mpc_controller.py:42)
+  const double* u_prev;  // [2]
+  double* warm;          // HBM slot, warm_size(N) doubles (ADMM iterate; also polish back-up)
+  double* scratch;       // HBM slot, warm_size(N) doubles (polished-solution back-up between passes)
+  double* u0;            // [2]
+  double* Xp;            // [4][N+1] state-major (visualization.py:244-245)
+  double* Up;            // [2][N]
+  int* status;           // OSQP status code
+  int* iters;
+  double* pri_res;
+  double* dua_res;
+  int* info;             // [4]: rho updates, factorisations, polish passes accepted, chain solves
+};
+
+struct Residuals { double pri, dua, eps_p, eps_d, sp, sd, nz, nq; };
+
+template <class Exec>
+MPC_HD Residuals compute_residuals(Exec& ex, const View& w, const Params& p, const Settings& s, double rho, int ymode) {
+  double r[7];
+  ex.reduce_max(w.N + 1, r, 7, [&](int k, double* rl) { residual_stage(w, p, rho, ymode, k, rl); });
+  Residuals o;
+  o.pri = r[0]; o.dua = r[3];
+  o.eps_p = s.eps_abs + s.eps_rel * dmax(r[1], r[2]);
+  o.eps_d = s.eps_abs + s.eps_rel * dmax(dmax(r[4], r[5]), r[6]);
+  o.sp = r[0] / (dmax(r[1], r[2]) + 1e-10);
+  o.sd = r[3] / (dmax(dmax(r[4], r[5]), r[6]) + 1e-10);
+  o.nz = dmax(r[1], r[2]); o.nq = dmax(dmax(r[4], r[5]), r[6]);
+  return o;
+}
+
+template <class Exec>
+MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settings& s, const ProblemIO& io) {
+  const int N = w.N;
+  const int NS = N + 1;
+  int n_rho = 0, n_fac = 0, n_solve = 0, n_pol = 0;
+
+  // ---- load + linearise ------------------------------------------------------------------
+  ex.single([&]() {
+    double* h = w.hdr();
+    for (int i = 0; i < 4; ++i) h[H_X0 + i] = io.x0[i];
+    for (int i = 0; i < 2; ++i) h[H_UPREV + i] = io.u_prev ? io.u_prev[i] : 0.0;
+    for (int i = 0; i < N + 2; ++i) w.act()[i] = 0;
+    unwrap_yaw(io.ref + 2, 4, NS, w.bx(0), 1);           // scratch: bx area holds the unwrapped yaw column
+  });
+  ex.stages(NS, [&](int k) { setup_stage(w, p, k, io.ref, w.bx(0)); });
+
+  // ---- initial iterate -------------------------------------------------------------------
+  double rho = s.rho0;
+  if (s.warm_start && io.warm) {
+    ex.stages(NS, [&](int k) { load_stage(w, k, io.warm); });
+    ex.single([&]() { for (int r = 0; r < 4; ++r) w.hdr()[H_YI + r] = io.warm[30 * NS + r]; });
+    rho = io.warm[30 * NS + 4];
+  } else {
+    ex.stages(NS, [&](int k) { cold_start_stage(w, p, k); });
+  }
+
+  Mode mode = admm_mode(rho, s);
+  ex.stages(NS, [&](int k) { assemble_stage(w, p, mode, k); });
+  ex.factor(w); ++n_fac;
+  ex.stages(NS, [&](int k) { admm_rhs_stage(w, p, s, rho, k); });
+
+  // ---- ADMM ------------------------------------------------------------------------------
+  int status = STATUS_UNSOLVED;
+  int it = 0;
+  Residuals res; res.pri = res.dua = 1e300; res.eps_p = res.eps_d = 0.0; res.sp = res.sd = 0.0; res.nz = res.nq = 0.0;
+  while (it < s.max_iter) {
+    ++it;
+    ex.solve(w); ++n_solve;
+    ex.stages(NS, [&](int k) { admm_update_stage(w, p, s, rho, k); admm_relax_x_stage(w, s, k); });
+    const bool check = (s.check_termination > 0) && (it % s.check_termination == 0);
+    const bool adapt = s.adaptive_rho && (s.adaptive_rho_interval > 0) && (it % s.adaptive_rho_interval == 0);
+    if (check || adapt) {
+      res = compute_residuals(ex, w, p, s, rho, 0);
+      if (check && res.pri <= res.eps_p && res.dua <= res.eps_d) { status = STATUS_SOLVED; break; }
+      if (adapt) {
+        double rho_new = rho * sqrt(res.sp / (res.sd + 1e-10));
+        rho_new = fmin(fmax(rho_new, s.rho_min), s.rho_max);
+        if (rho_new > rho * s.adaptive_rho_tolerance || rho_new < rho / s.adaptive_rho_tolerance) {
+          ex.stages(NS, [&](int k) { rescale_v_stage(w, p, rho, rho_new, k); });
+          rho = rho_new; ++n_rho;
+          mode = admm_mode(rho, s);
+          ex.stages(NS, [&](int k) { assemble_stage(w, p, mode, k); });
+          ex.factor(w); ++n_fac;
+        }
+      }
+    }
+    ex.stages(NS, [&](int k) { admm_rhs_stage(w, p, s, rho, k); });
+  }
+  if (status != STATUS_SOLVED) {
+    res = compute_residuals(ex, w, p, s, rho, 0);
+    if (res.pri <= res.eps_p && res.dua <= res.eps_d) status = STATUS_SOLVED;
+    else {
+      double ep10 = 10.0 * s.eps_abs + 10.0 * (res.eps_p - s.eps_abs);
+      double ed10 = 10.0 * s.eps_abs + 10.0 * (res.eps_d - s.eps_abs);
+      status = (res.pri <= ep10 && res.dua <= ed10) ? STATUS_SOLVED_INACCURATE : STATUS_MAX_ITER;
+    }
+  }
+  double pri = res.pri, dua = res.dua;
+
+  // ---- keep the ADMM iterate in HBM (warm start of the next call; polish back-up) ---------
+  if (io.warm) {
+    ex.stages(NS, [&](int k) { save_stage(w, k, io.warm); });
+    ex.single([&]() {
+      for (int r = 0; r < 4; ++r) io.warm[30 * NS + r] = w.hdr()[H_YI + r];
+      io.warm[30 * NS + 4] = rho;
+    });
+  }
+
+  // ---- polish (OSQP polish = pass 1; further passes re-identify the active set from Ax + y) ----
+  if (status == STATUS_SOLVED && s.polish_passes > 0 && io.warm && io.scratch) {
+    const Mode pm = polish_mode(s);
+    for (int pass = 0; pass < s.polish_passes; ++pass) {
+      if (pass > 0) {
+        ex.stages(NS, [&](int k) { save_stage(w, k, io.scratch); });
+        ex.single([&]() { for (int r = 0; r < 4; ++r) io.scratch[30 * NS + r] = w.hdr()[H_YI + r]; });
+      }
+      int changed = ex.any(NS, [&](int k) { return polish_activity_stage(w, p, rho, pass == 0, k); });
+      if (pass > 0 && !changed) break;
+      ex.stages(NS, [&](int k) { polish_zero_stage(w, k); });
+      ex.stages(NS, [&](int k) { assemble_stage(w, p, pm, k); });
+      ex.factor(w); ++n_fac;
+      for (int step = 0; step <= s.polish_refine_iter; ++step) {
+        ex.stages(NS, [&](int k) { polish_rhs_stage(w, p, pm, k); });
+        ex.solve(w); ++n_solve;
+        ex.stages(NS, [&](int k) { polish_dual_stage(w, p, pm, k); });
+        ex.stages(NS, [&](int k) { polish_primal_stage(w, k); });
+      }
+      Residuals rp = compute_residuals(ex, w, p, s, rho, 1);
+      bool ok;
+      if (pass == 0) {
+        ok = (rp.pri < pri && rp.dua < dua) || (rp.pri < pri && dua < 1e-10) || (rp.dua < dua && pri < 1e-10);
+      } else {
+        ok = rp.pri <= dmax(10.0 * pri, 1e-9 * dmax(1.0, res.nz)) && rp.dua <= dmax(10.0 * dua, 1e-9 * dmax(1.0, res.nq));
+      }
+      if (ok) { pri = rp.pri; dua = rp.dua; n_pol = pass + 1; }
+      else {
+        const double* src = pass == 0 ? io.warm : io.scratch;
+        ex.stages(NS, [&](int k) { load_stage(w, k, src); });
+        ex.single([&]() { for (int r = 0; r < 4; ++r) w.hdr()[H_YI + r] = src[30 * NS + r]; });
+        break;
+      }
+    }
+  }
+
+  // ---- outputs (mpc_controller.py:141: U[:,0], X (4,N+1), U (2,N)) --------------------------
+  ex.stages(NS, [&](int k) {
+    const double* rc = w.rec(k);
+    for (int j = 0; j < 4; ++j) io.Xp[j * NS + k] = rc[R_XU + j];
+    if (k < N) { io.Up[k] = rc[R_XU + 4]; io.Up[N + k] = rc[R_XU + 5]; }
+    if (k == 0) {
+      io.u0[0] = rc[R_XU + 4]; io.u0[1] = rc[R_XU + 5];
+      *io.status = status; *io.iters = it;
+      if (io.pri_res) *io.pri_res = pri;
+      if (io.dua_res) *io.dua_res = dua;
+      if (io.info) { io.info[0] = n_rho; io.info[1] = n_fac; io.info[2] = n_pol; io.info[3] = n_solve; }
+    }
+  });
+}
+
+}  // namespace mpc

@@ -1,0 +1,107 @@
+// Lane-emulation harness (TEST INFRASTRUCTURE, host only): runs the very same per-problem driver that
+// the CUDA kernel runs (rrt_mpc_b200/csrc/mpc_solve.h) with a sequential execution policy, so that the
+// index logic can be debugged and hazard-checked (forward vs reverse stage order must agree bit for
+// bit) in a container without a GPU.  Never linked into libcudampc.so and never used by the product.
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../rrt_mpc_b200/csrc/mpc_solve.h"
+
+using namespace mpc;
+
+struct EmuExec {
+  int reverse;
+  template <class F> void stages(int n, F f) {
+    if (!reverse) for (int k = 0; k < n; ++k) f(k);
+    else for (int k = n - 1; k >= 0; --k) f(k);
+  }
+  template <class F> void single(F f) { f(); }
+  template <class F> void reduce_max(int n, double* r, int nr, F f) {
+    for (int i = 0; i < nr; ++i) r[i] = 0.0;
+    stages(n, [&](int k) { f(k, r); });
+  }
+  template <class F> int any(int n, F f) {
+    int a = 0;
+    stages(n, [&](int k) { a |= f(k); });
+    return a;
+  }
+  void factor(const View& w) { factor_band(w); }
+  void solve(const View& w) { chain_solve(w); }
+};
+
+extern "C" {
+
+int emu_footprint(int N) { return footprint(N); }
+int emu_warm_size(int N) { return warm_size(N); }
+
+// params/settings passed as flat double arrays to keep the ctypes side trivial
+//  par: L, dt, q[4], r[2], qn[4], u_lo[2], u_hi[2], v_lo, v_hi, du_lo[2], du_hi[2], w_v, w_u, w_du   (25)
+//  set: eps_abs, eps_rel, rho0, alpha, sigma, adaptive_rho_tolerance, rho_eq_factor, rho_min, rho_max, delta,
+//       max_iter, check_termination, adaptive_rho, adaptive_rho_interval, polish_passes, polish_refine_iter, warm_start (17)
+static void unpack(const double* par, const double* set, int N, Params& p, Settings& s) {
+  int i = 0;
+  p.L = par[i++]; p.dt = par[i++];
+  for (int j = 0; j < 4; ++j) p.q[j] = par[i++];
+  for (int j = 0; j < 2; ++j) p.r[j] = par[i++];
+  for (int j = 0; j < 4; ++j) p.qn[j] = par[i++];
+  for (int j = 0; j < 2; ++j) p.u_lo[j] = par[i++];
+  for (int j = 0; j < 2; ++j) p.u_hi[j] = par[i++];
+  p.v_lo = par[i++]; p.v_hi = par[i++];
+  for (int j = 0; j < 2; ++j) p.du_lo[j] = par[i++];
+  for (int j = 0; j < 2; ++j) p.du_hi[j] = par[i++];
+  p.w_v = par[i++]; p.w_u = par[i++]; p.w_du = par[i++];
+  p.N = N;
+  i = 0;
+  s.eps_abs = set[i++]; s.eps_rel = set[i++]; s.rho0 = set[i++]; s.alpha = set[i++]; s.sigma = set[i++];
+  s.adaptive_rho_tolerance = set[i++]; s.rho_eq_factor = set[i++]; s.rho_min = set[i++]; s.rho_max = set[i++];
+  s.delta = set[i++];
+  s.max_iter = (int)set[i++]; s.check_termination = (int)set[i++]; s.adaptive_rho = (int)set[i++];
+  s.adaptive_rho_interval = (int)set[i++]; s.polish_passes = (int)set[i++]; s.polish_refine_iter = (int)set[i++];
+  s.warm_start = (int)set[i++];
+}
+
+int emu_solve_batch(const double* par, const double* set, int N, int B, int reverse,
+                    const double* x0, const double* ref, const double* u_prev, double* warm,
+                    double* u0, double* Xp, double* Up, int* status, int* iters, double* pri, double* dua, int* info) {
+  Params p; Settings s; unpack(par, set, N, p, s);
+  std::vector<double> ws(footprint(N)), scratch(warm_size(N)), warm_local(warm_size(N));
+  for (int b = 0; b < B; ++b) {
+    std::fill(ws.begin(), ws.end(), 0.0);
+    View w{ws.data(), N};
+    ProblemIO io;
+    io.x0 = x0 + 4 * b; io.ref = ref + (size_t)4 * (N + 1) * b; io.u_prev = u_prev ? u_prev + 2 * b : nullptr;
+    io.warm = warm ? warm + (size_t)warm_size(N) * b : warm_local.data();
+    io.scratch = scratch.data();
+    io.u0 = u0 + 2 * b; io.Xp = Xp + (size_t)4 * (N + 1) * b; io.Up = Up + (size_t)2 * N * b;
+    io.status = status + b; io.iters = iters + b; io.pri_res = pri + b; io.dua_res = dua + b; io.info = info + 4 * b;
+    Settings sb = s;
+    if (!warm) sb.warm_start = 0;
+    EmuExec ex{reverse};
+    solve_problem(ex, w, p, sb, io);
+  }
+  return 0;
+}
+
+// linearisation hook: A (B,N,4,4), Bm (B,N,4,2), c (B,N,4) exactly as the solve path computes them
+int emu_linearize_batch(const double* par, const double* set, int N, int B, const double* ref, double* A, double* Bm, double* c) {
+  Params p; Settings s; unpack(par, set, N, p, s);
+  std::vector<double> uy(N + 1);
+  for (int b = 0; b < B; ++b) {
+    const double* r = ref + (size_t)4 * (N + 1) * b;
+    unwrap_yaw(r + 2, 4, N + 1, uy.data(), 1);
+    for (int k = 0; k < N; ++k) {
+      int kl = k > 0 ? k - 1 : 0;
+      double lin[7];
+      linearize_point(p, r[4 * kl], r[4 * kl + 1], uy[kl], r[4 * kl + 3], lin);
+      double* a = A + ((size_t)b * N + k) * 16; double* bm = Bm + ((size_t)b * N + k) * 8; double* cc = c + ((size_t)b * N + k) * 4;
+      for (int i = 0; i < 16; ++i) a[i] = 0.0;
+      for (int i = 0; i < 8; ++i) bm[i] = 0.0;
+      a[0] = a[5] = a[10] = a[15] = 1.0;
+      a[2] = lin[0]; a[3] = lin[1]; a[6] = lin[2]; a[7] = lin[3];
+      bm[2 * 2 + 1] = lin[4]; bm[3 * 2 + 0] = p.dt;
+      cc[0] = lin[5]; cc[1] = lin[6]; cc[2] = 0.0; cc[3] = 0.0;
+    }
+  }
+  return 0;
+}
+}
