@@ -1,0 +1,645 @@
+// cudampc.cu — libcudampc.so: CUDA kernels (sm_100a) + C ABI (include/cudampc.h).
+//
+// One warp owns one tracking problem; the whole problem (ADMM iterate, linearisation, banded LDL' factor,
+// right-hand side) lives in shared memory for the entire solve (DESIGN.md §data layout).  Stage-parallel
+// phases run with lanes striding over the N+1 stages; the banded factorisation / triangular sweeps are
+// the sequential chain.  Warps fetch problems from a global counter, so a launch is persistent:
+// grid = SMs x resident-problems-per-SM regardless of the batch size.
+//
+// There is no CPU fallback: every entry point fails with CUDAMPC_ERR_CUDA if the device is unusable.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+
+#include "../../include/cudampc.h"
+#include "mpc_solve.h"
+
+using namespace mpc;
+
+// ------------------------------------------------------------------------------------------------
+// Warp execution policy
+// ------------------------------------------------------------------------------------------------
+struct WarpExec {
+  int lane;
+  __device__ __forceinline__ void tag(int) {}
+  template <class F> __device__ __forceinline__ void stages(int n, F f) {
+    for (int k = lane; k < n; k += 32) f(k);
+    __syncwarp();
+  }
+  template <class F> __device__ __forceinline__ void single(F f) {
+    if (lane == 0) f();
+    __syncwarp();
+  }
+  template <class F> __device__ __forceinline__ void reduce_max(int n, double* r, int nr, F f) {
+    for (int i = 0; i < nr; ++i) r[i] = 0.0;
+    for (int k = lane; k < n; k += 32) f(k, r);
+    for (int i = 0; i < nr; ++i) {
+      double v = r[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+      r[i] = v;
+    }
+    __syncwarp();
+  }
+  template <class F> __device__ __forceinline__ int any(int n, F f) {
+    int a = 0;
+    for (int k = lane; k < n; k += 32) a |= f(k);
+    a = __any_sync(0xffffffffu, a);
+    __syncwarp();
+    return a;
+  }
+  __device__ __forceinline__ void factor(const View& w) {
+    if (lane == 0) factor_band(w);
+    __syncwarp();
+  }
+  __device__ __forceinline__ void solve(const View& w) {
+    if (lane == 0) chain_solve(w);
+    __syncwarp();
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// CTA execution policy ("transposed chain"): the CTA holds P problems, warp p runs the stage-parallel
+// phases of problem p, and the sequential triangular sweeps of ALL P problems run in lock step in warp 0
+// with lanes = problems (one DFMA warp-instruction then serves P problems instead of one lane).  A chain
+// operation is a rendezvous round: [bar] warp 0 sweeps every problem that posted a request [bar].
+// Factorisations run in the owner warp, chunked over rounds, overlapped with the other problems' sweeps.
+// ------------------------------------------------------------------------------------------------
+struct CtaShared {
+  int req[32];
+  int active;      // warps that still have work; read only between the two barriers of a round
+};
+
+__device__ __forceinline__ void cta_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+
+struct CtaExec {
+  int lane, warp, P, N, F;
+  double* smem0;
+  CtaShared* sh;
+  int chunk;       // factor stages per round
+  __device__ __forceinline__ void tag(int) {}
+  template <class Fn> __device__ __forceinline__ void stages(int n, Fn f) {
+    for (int k = lane; k < n; k += 32) f(k);
+    __syncwarp();
+  }
+  template <class Fn> __device__ __forceinline__ void single(Fn f) {
+    if (lane == 0) f();
+    __syncwarp();
+  }
+  template <class Fn> __device__ __forceinline__ void reduce_max(int n, double* r, int nr, Fn f) {
+    for (int i = 0; i < nr; ++i) r[i] = 0.0;
+    for (int k = lane; k < n; k += 32) f(k, r);
+    for (int i = 0; i < nr; ++i) {
+      double v = r[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+      r[i] = v;
+    }
+    __syncwarp();
+  }
+  template <class Fn> __device__ __forceinline__ int any(int n, Fn f) {
+    int a = 0;
+    for (int k = lane; k < n; k += 32) a |= f(k);
+    a = __any_sync(0xffffffffu, a);
+    __syncwarp();
+    return a;
+  }
+  // one rendezvous round; kind 0 none, 1 sweep request, 2 factor chunk [i0,i1) in the owner warp
+  __device__ __forceinline__ int round(int kind, const View& w, int i0, int i1) {
+    if (lane == 0) sh->req[warp] = (kind == 1);
+    cta_bar(32 * P);
+    const int snap = sh->active;
+    if (warp == 0) {
+      if (lane < P && sh->req[lane]) { View v{smem0 + (size_t)lane * F, N}; chain_solve(v); }
+      if (kind == 2 && lane == 0) factor_stages(w, i0, i1);
+      __syncwarp();
+    } else if (kind == 2 && lane == 0) {
+      factor_stages(w, i0, i1);
+    }
+    cta_bar(32 * P);
+    return snap;
+  }
+  __device__ __forceinline__ void solve(const View& w) { round(1, w, 0, 0); }
+  __device__ __forceinline__ void factor(const View& w) {
+    const int n = N + 1;
+    for (int i0 = 0; i0 < n; i0 += chunk) round(2, w, i0, min(i0 + chunk, n));
+  }
+  __device__ __forceinline__ void drain() {
+    if (lane == 0) atomicSub(&sh->active, 1);
+    while (round(0, View{smem0, N}, 0, 0) > 0) {}
+  }
+};
+
+struct BatchArgs {
+  const double* x0; const double* ref; const double* u_prev;
+  double* warm; double* scratch;
+  double* u0; double* Xp; double* Up; int* status; int* iters; double* pri; double* dua; int* info;
+  int* counter;
+  int batch;
+};
+
+__device__ __forceinline__ int next_problem(int* counter, int lane) {
+  int p = 0;
+  if (lane == 0) p = atomicAdd(counter, 1);
+  return __shfl_sync(0xffffffffu, p, 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_solve: batched MPCController.solve
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) mpc_solve_kernel(Params p, Settings s, BatchArgs a) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31;
+  const int N = p.N;
+  View w{smem, N};
+  WarpExec ex{lane};
+  const int ws = warm_size(N);
+  for (int b = next_problem(a.counter, lane); b < a.batch; b = next_problem(a.counter, lane)) {
+    ProblemIO io;
+    io.x0 = a.x0 + 4 * (size_t)b;
+    io.ref = RefWin{a.ref + (size_t)4 * (N + 1) * b, 0, N + 1, 1.0};
+    io.u_prev = a.u_prev ? a.u_prev + 2 * (size_t)b : nullptr;
+    io.warm = a.warm + (size_t)ws * b;
+    io.scratch = a.scratch + (size_t)ws * b;
+    io.u0 = a.u0 + 2 * (size_t)b;
+    io.Xp = a.Xp + (size_t)4 * (N + 1) * b;
+    io.Up = a.Up + (size_t)2 * N * b;
+    io.status = a.status + b; io.iters = a.iters + b;
+    io.pri_res = a.pri ? a.pri + b : nullptr; io.dua_res = a.dua ? a.dua + b : nullptr;
+    io.info = a.info ? a.info + 4 * (size_t)b : nullptr;
+    solve_problem(ex, w, p, s, io);
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(512) mpc_solve_cta_kernel(Params p, Settings s, BatchArgs a, int P, int F, int chunk) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int N = p.N;
+  CtaShared* sh = reinterpret_cast<CtaShared*>(smem + (size_t)P * F);
+  if (threadIdx.x == 0) sh->active = P;
+  if (threadIdx.x < 32) sh->req[threadIdx.x] = 0;
+  __syncthreads();
+  View w{smem + (size_t)warp * F, N};
+  CtaExec ex{lane, warp, P, N, F, smem, sh, chunk};
+  const int ws = warm_size(N);
+  for (int b = next_problem(a.counter, lane); b < a.batch; b = next_problem(a.counter, lane)) {
+    ProblemIO io;
+    io.x0 = a.x0 + 4 * (size_t)b;
+    io.ref = RefWin{a.ref + (size_t)4 * (N + 1) * b, 0, N + 1, 1.0};
+    io.u_prev = a.u_prev ? a.u_prev + 2 * (size_t)b : nullptr;
+    io.warm = a.warm + (size_t)ws * b;
+    io.scratch = a.scratch + (size_t)ws * b;
+    io.u0 = a.u0 + 2 * (size_t)b;
+    io.Xp = a.Xp + (size_t)4 * (N + 1) * b;
+    io.Up = a.Up + (size_t)2 * N * b;
+    io.status = a.status + b; io.iters = a.iters + b;
+    io.pri_res = a.pri ? a.pri + b : nullptr; io.dua_res = a.dua ? a.dua + b : nullptr;
+    io.info = a.info ? a.info + 4 * (size_t)b : nullptr;
+    solve_problem(ex, w, p, s, io);
+    __syncwarp();
+  }
+  ex.drain();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_lin: batched linearisation hook (parity at 1e-12 against vehicle_model.linearize)
+// ------------------------------------------------------------------------------------------------
+__global__ void mpc_linearize_kernel(Params p, int batch, const double* ref, double* A, double* Bm, double* c) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int N = p.N;
+  double* uy = smem + (size_t)wid * (N + 1);
+  for (int b = blockIdx.x * wpb + wid; b < batch; b += gridDim.x * wpb) {
+    RefWin rw{ref + (size_t)4 * (N + 1) * b, 0, N + 1, 1.0};
+    if (lane == 0) unwrap_window(rw, N + 1, uy);
+    __syncwarp();
+    for (int k = lane; k < N; k += 32) {
+      int kl = k > 0 ? k - 1 : 0;
+      const double* r = rw.row(kl);
+      double lin[7];
+      linearize_point(p, r[0], r[1], uy[kl], r[3], lin);
+      double* a = A + ((size_t)b * N + k) * 16;
+      double* bm = Bm + ((size_t)b * N + k) * 8;
+      double* cc = c + ((size_t)b * N + k) * 4;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] = 0.0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) bm[i] = 0.0;
+      a[0] = a[5] = a[10] = a[15] = 1.0;
+      a[2] = lin[0]; a[3] = lin[1]; a[6] = lin[2]; a[7] = lin[3];
+      bm[5] = lin[4]; bm[6] = p.dt;
+      cc[0] = lin[5]; cc[1] = lin[6]; cc[2] = 0.0; cc[3] = 0.0;
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_rollout: TrajectoryTracker.track for a batch of vehicles, all steps on the device
+// ------------------------------------------------------------------------------------------------
+struct RolloutArgs {
+  const double* ref_global; const int* ref_len; int ref_stride;
+  const double* state0; const double* goal;
+  double* warm; double* scratch; double* work;   // work: per vehicle 16 doubles (state, u_prev, u0 out) + Xp/Up scratch
+  double* states; double* controls; int* n_steps; int* flags; int* step_status; int* step_iters;
+  int* counter; int batch;
+};
+
+__device__ __forceinline__ void f_discrete_dev(const Params& p, const double* x, const double* u, double* out) {
+  // vehicle_model.py:11-21
+  double yaw = x[2], v = x[3];
+  out[0] = x[0] + p.dt * v * cos(yaw + 0.0);
+  out[1] = x[1] + p.dt * v * sin(yaw + 0.0);
+  out[2] = yaw + p.dt * (v / p.L) * tan(u[1]);
+  out[3] = v + p.dt * u[0];
+}
+
+__global__ void __launch_bounds__(32) mpc_rollout_kernel(Params p, Settings s, cudampc_rollout_cfg cfg, RolloutArgs a) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31;
+  const int N = p.N;
+  View w{smem, N};
+  WarpExec ex{lane};
+  const int ws = warm_size(N);
+  const int wk = 16 + 4 * (N + 1) + 2 * N;   // per-vehicle global scratch
+  const double nan_ = __longlong_as_double(0x7ff8000000000000LL);
+  for (int b = next_problem(a.counter, lane); b < a.batch; b = next_problem(a.counter, lane)) {
+    double* wkb = a.work + (size_t)wk * b;   // [0..3] state, [4..5] u_prev, [6..7] u0, [8] pri, [9] dua, [10..13] info(int), 16.. Xp, Up
+    const double* refg = a.ref_global + (size_t)4 * a.ref_stride * b;
+    const int len = a.ref_len[b];
+    if (lane == 0) {
+      for (int i = 0; i < 4; ++i) wkb[i] = a.state0[4 * (size_t)b + i];
+      wkb[4] = 0.0; wkb[5] = 0.0;
+    }
+    __syncwarp();
+    int path_idx = 0, flags = 0, nst = 0;
+    for (int step = 0; step < cfg.sim_steps; ++step) {
+      int* st_out = a.step_status ? a.step_status + (size_t)cfg.sim_steps * b + step : reinterpret_cast<int*>(wkb + 10);
+      int* it_out = a.step_iters ? a.step_iters + (size_t)cfg.sim_steps * b + step : reinterpret_cast<int*>(wkb + 10) + 1;
+      ProblemIO io;
+      io.x0 = wkb; io.u_prev = wkb + 4;
+      io.ref = RefWin{refg, path_idx, len, 1.0};
+      io.warm = a.warm + (size_t)ws * b; io.scratch = a.scratch + (size_t)ws * b;
+      io.u0 = wkb + 6; io.Xp = wkb + 16; io.Up = wkb + 16 + 4 * (N + 1);
+      io.status = st_out; io.iters = it_out; io.pri_res = nullptr; io.dua_res = nullptr; io.info = nullptr;
+      Settings ss = s;
+      ss.warm_start = (s.warm_start && step > 0) ? 1 : 0;
+      solve_problem(ex, w, p, ss, io);
+      __syncwarp();
+      int status = *st_out;
+      if (status != STATUS_SOLVED && status != STATUS_SOLVED_INACCURATE && cfg.relax_on_failure) {
+        // control_stage.py:45-56: v_ref *= 0.6, du_bounds widened, one cold retry
+        Params pr = p;
+        pr.du_lo[0] -= cfg.relax_da; pr.du_hi[0] += cfg.relax_da;
+        pr.du_lo[1] -= cfg.relax_ddelta; pr.du_hi[1] += cfg.relax_ddelta;
+        io.ref.vscale = cfg.relax_v_scale;
+        ss.warm_start = 0;
+        solve_problem(ex, w, pr, ss, io);
+        __syncwarp();
+        status = *st_out;
+      }
+      if (status != STATUS_SOLVED && status != STATUS_SOLVED_INACCURATE) { flags |= 2; break; }
+      // integrate, carry u_prev, path index rule, goal test (control_stage.py:127-150)
+      double xn[4];
+      f_discrete_dev(p, wkb, wkb + 6, xn);
+      double u0a = wkb[6], u0d = wkb[7];
+      __syncwarp();
+      if (lane == 0) {
+        for (int i = 0; i < 4; ++i) { wkb[i] = xn[i]; a.states[((size_t)cfg.sim_steps * b + step) * 4 + i] = xn[i]; }
+        wkb[4] = u0a; wkb[5] = u0d;
+        if (a.controls) { a.controls[((size_t)cfg.sim_steps * b + step) * 2] = u0a; a.controls[((size_t)cfg.sim_steps * b + step) * 2 + 1] = u0d; }
+      }
+      __syncwarp();
+      nst = step + 1;
+      if (path_idx < len - 2) {
+        double dx = xn[0] - refg[4 * (size_t)path_idx], dy = xn[1] - refg[4 * (size_t)path_idx + 1];
+        if (dx * dx + dy * dy > cfg.advance_dist2) path_idx += 1;
+      }
+      if (hypot(xn[0] - a.goal[2 * (size_t)b], xn[1] - a.goal[2 * (size_t)b + 1]) < cfg.goal_radius) { flags |= 1; break; }
+    }
+    // rows after the vehicle stopped
+    for (int i = nst * 4 + lane; i < cfg.sim_steps * 4; i += 32) a.states[(size_t)cfg.sim_steps * b * 4 + i] = nan_;
+    if (a.controls) for (int i = nst * 2 + lane; i < cfg.sim_steps * 2; i += 32) a.controls[(size_t)cfg.sim_steps * b * 2 + i] = nan_;
+    if (a.step_status) for (int i = nst + (flags & 2 ? 1 : 0) + lane; i < cfg.sim_steps; i += 32) a.step_status[(size_t)cfg.sim_steps * b + i] = 0;
+    if (a.step_iters) for (int i = nst + (flags & 2 ? 1 : 0) + lane; i < cfg.sim_steps; i += 32) a.step_iters[(size_t)cfg.sim_steps * b + i] = 0;
+    if (lane == 0) { a.n_steps[b] = nst; a.flags[b] = flags; }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Handle + C ABI
+// ------------------------------------------------------------------------------------------------
+struct cudampc_handle {
+  int device, max_batch, N;
+  Params p;
+  double *warm, *scratch, *work;
+  int* counter;
+  // staging for the host-pointer entry point
+  double *h_in, *h_out, *d_in, *d_out;
+  size_t in_doubles, out_doubles;
+  int sms, per_sm, smem_bytes;
+  int cta_P, cta_smem, cta_chunk, use_cta;
+  long long launches;
+  char err[512];
+};
+
+static char g_create_err[512] = "";
+
+static int fail(cudampc_handle* h, int code, const char* fmt, const char* detail) {
+  char* dst = h ? h->err : g_create_err;
+  snprintf(dst, 512, fmt, detail ? detail : "");
+  return code;
+}
+#define CU(h, call)                                                                         \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      char buf_[400];                                                                       \
+      snprintf(buf_, sizeof buf_, "%s -> %s", #call, cudaGetErrorString(e_));              \
+      return fail(h, CUDAMPC_ERR_CUDA, "CUDA failure: %s", buf_);                          \
+    }                                                                                       \
+  } while (0)
+
+static bool is_diag(const double* m, int n) {
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j)
+      if (i != j && m[i * n + j] != 0.0) return false;
+  return true;
+}
+
+static int convert_params(const cudampc_params* in, Params* p, cudampc_handle* h) {
+  if (!in) return fail(h, CUDAMPC_ERR_INVALID, "%s", "params is NULL");
+  if (in->horizon < 1 || in->horizon > 256) return fail(h, CUDAMPC_ERR_INVALID, "%s", "horizon must be in [1, 256]");
+  if (!(in->dt > 0.0) || !(in->wheelbase_px > 0.0)) return fail(h, CUDAMPC_ERR_INVALID, "%s", "dt and wheelbase_px must be > 0");
+  if (!is_diag(in->q, 4) || !is_diag(in->r, 2) || !is_diag(in->q_terminal, 4))
+    return fail(h, CUDAMPC_ERR_UNSUPPORTED, "%s", "non-diagonal q / r / q_terminal are not supported by this build");
+  p->L = in->wheelbase_px; p->dt = in->dt; p->N = in->horizon;
+  for (int i = 0; i < 4; ++i) { p->q[i] = in->q[5 * i]; p->qn[i] = in->q_terminal[5 * i]; }
+  for (int i = 0; i < 2; ++i) p->r[i] = in->r[3 * i];
+  for (int i = 0; i < 4; ++i) if (!(p->q[i] > 0.0) || !(p->qn[i] > 0.0)) return fail(h, CUDAMPC_ERR_INVALID, "%s", "q and q_terminal diagonals must be > 0");
+  for (int i = 0; i < 2; ++i) if (!(p->r[i] > 0.0)) return fail(h, CUDAMPC_ERR_INVALID, "%s", "r diagonal must be > 0");
+  p->u_lo[0] = in->u_bounds[0]; p->u_hi[0] = in->u_bounds[1]; p->u_lo[1] = in->u_bounds[2]; p->u_hi[1] = in->u_bounds[3];
+  p->v_lo = in->v_bounds[0]; p->v_hi = in->v_bounds[1];
+  p->du_lo[0] = in->du_bounds[0]; p->du_hi[0] = in->du_bounds[1]; p->du_lo[1] = in->du_bounds[2]; p->du_hi[1] = in->du_bounds[3];
+  p->w_v = in->slack_velocity; p->w_u = in->slack_input; p->w_du = in->slack_rate;
+  if (!(p->w_v > 0.0) || !(p->w_u > 0.0) || !(p->w_du > 0.0)) return fail(h, CUDAMPC_ERR_INVALID, "%s", "slack weights must be > 0");
+  return CUDAMPC_OK;
+}
+
+static int convert_settings(const cudampc_settings* in, Settings* s, cudampc_handle* h) {
+  cudampc_settings d;
+  if (!in) { cudampc_default_settings(&d); in = &d; }
+  if (!(in->eps_abs >= 0.0) || !(in->eps_rel >= 0.0) || !(in->rho > 0.0) || !(in->alpha > 0.0 && in->alpha < 2.0) ||
+      !(in->sigma > 0.0) || in->max_iter < 1 || !(in->delta > 0.0))
+    return fail(h, CUDAMPC_ERR_INVALID, "%s", "settings out of range");
+  s->eps_abs = in->eps_abs; s->eps_rel = in->eps_rel; s->rho0 = in->rho; s->alpha = in->alpha; s->sigma = in->sigma;
+  s->adaptive_rho_tolerance = in->adaptive_rho_tolerance; s->rho_eq_factor = in->rho_eq_factor;
+  s->rho_min = in->rho_min; s->rho_max = in->rho_max; s->delta = in->delta;
+  s->max_iter = in->max_iter; s->check_termination = in->check_termination; s->adaptive_rho = in->adaptive_rho;
+  s->adaptive_rho_interval = in->adaptive_rho_interval; s->polish_passes = in->polish_passes;
+  s->polish_refine_iter = in->polish_refine_iter; s->warm_start = in->warm_start;
+  return CUDAMPC_OK;
+}
+
+extern "C" {
+
+int cudampc_version(void) { return CUDAMPC_VERSION; }
+
+void cudampc_default_settings(cudampc_settings* s) {
+  if (!s) return;
+  memset(s, 0, sizeof *s);
+  s->eps_abs = 1e-3; s->eps_rel = 1e-3; s->rho = 0.1; s->alpha = 1.6;       /* mpc_controller.py:121-131 */
+  s->sigma = 1e-6; s->adaptive_rho_tolerance = 5.0; s->rho_eq_factor = 1e3; s->rho_min = 1e-6; s->rho_max = 1e6;
+  s->delta = 1e-6; s->max_iter = 60000; s->check_termination = 25; s->adaptive_rho = 1; s->adaptive_rho_interval = 50;
+  s->polish_passes = 1; s->polish_refine_iter = 3; s->warm_start = 0;
+}
+
+void cudampc_default_rollout_cfg(cudampc_rollout_cfg* c) {
+  if (!c) return;
+  memset(c, 0, sizeof *c);
+  c->sim_steps = 300; c->relax_on_failure = 1; c->advance_dist2 = 25.0; c->goal_radius = 8.0;
+  c->relax_v_scale = 0.6; c->relax_da = 5.0; c->relax_ddelta = 0.05;
+}
+
+const char* cudampc_last_error(const cudampc_handle* h) { return h ? h->err : g_create_err; }
+
+int cudampc_create(const cudampc_params* params, int max_batch, int device, cudampc_handle** out) {
+  if (!out) return fail(nullptr, CUDAMPC_ERR_INVALID, "%s", "out is NULL");
+  *out = nullptr;
+  if (max_batch < 1) return fail(nullptr, CUDAMPC_ERR_INVALID, "%s", "max_batch must be >= 1");
+  Params p;
+  int rc = convert_params(params, &p, nullptr);
+  if (rc) return rc;
+  int ndev = 0;
+  CU(nullptr, cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(nullptr, CUDAMPC_ERR_INVALID, "%s", "device index out of range");
+  CU(nullptr, cudaSetDevice(device));
+  cudampc_handle* h = new (std::nothrow) cudampc_handle();
+  if (!h) return fail(nullptr, CUDAMPC_ERR_NOMEM, "%s", "host allocation failed");
+  memset(h, 0, sizeof *h);
+  h->device = device; h->max_batch = max_batch; h->N = p.N; h->p = p;
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { delete h; return fail(nullptr, CUDAMPC_ERR_CUDA, "CUDA failure: %s", cudaGetErrorString(e)); }
+  h->sms = prop.multiProcessorCount;
+  h->smem_bytes = footprint(p.N) * (int)sizeof(double);
+  const int optin = (int)prop.sharedMemPerBlockOptin;
+  if (h->smem_bytes > optin) { delete h; return fail(nullptr, CUDAMPC_ERR_UNSUPPORTED, "%s", "horizon too long for one problem per 227 KB of shared memory"); }
+  e = cudaFuncSetAttribute(mpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes);
+  int occ = 0;
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mpc_solve_kernel, 32, h->smem_bytes);
+  if (e != cudaSuccess || occ < 1) { delete h; return fail(nullptr, CUDAMPC_ERR_CUDA, "CUDA failure: %s", cudaGetErrorString(e)); }
+  h->per_sm = occ;
+  // transposed-chain kernel: one CTA per SM holding P problems (P <= 16: 512 threads x 128 registers)
+  {
+    const int F = footprint(p.N);
+    int P = (optin - (int)sizeof(CtaShared) - 64) / (F * (int)sizeof(double));
+    if (P > 16) P = 16;
+    h->cta_P = P;
+    h->cta_smem = P * F * (int)sizeof(double) + (int)sizeof(CtaShared) + 16;
+    h->cta_chunk = (p.N + 1 + 2) / 3;        // a factorisation spreads over 3 rounds
+    const char* env = getenv("CUDAMPC_KERNEL");
+    h->use_cta = (P >= 2) && !(env && strcmp(env, "warp") == 0);
+    if (h->use_cta) {
+      e = cudaFuncSetAttribute(mpc_solve_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta_smem);
+      if (e != cudaSuccess) { delete h; return fail(nullptr, CUDAMPC_ERR_CUDA, "CUDA failure: %s", cudaGetErrorString(e)); }
+      h->per_sm = P;
+    }
+  }
+  const size_t ws = (size_t)warm_size(p.N) * max_batch * sizeof(double);
+  const size_t wk = (size_t)(16 + 4 * (p.N + 1) + 2 * p.N) * max_batch * sizeof(double);
+  h->in_doubles = (size_t)max_batch * (4 + 4 * (p.N + 1) + 2);
+  h->out_doubles = (size_t)max_batch * (2 + 4 * (p.N + 1) + 2 * p.N + 2 + 4);   // + pri, dua, (status, iters, info[4] as int32 in 3 doubles.. rounded to 4)
+  e = cudaMalloc(&h->warm, ws);
+  if (e == cudaSuccess) e = cudaMalloc(&h->scratch, ws);
+  if (e == cudaSuccess) e = cudaMalloc(&h->work, wk);
+  if (e == cudaSuccess) e = cudaMalloc(&h->counter, sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_in, h->in_doubles * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_out, h->out_doubles * sizeof(double));
+  if (e == cudaSuccess) e = cudaMallocHost(&h->h_in, h->in_doubles * sizeof(double));
+  if (e == cudaSuccess) e = cudaMallocHost(&h->h_out, h->out_doubles * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemset(h->warm, 0, ws);
+  if (e != cudaSuccess) {
+    snprintf(g_create_err, sizeof g_create_err, "CUDA failure: allocation -> %s", cudaGetErrorString(e));
+    cudampc_destroy(h);
+    return CUDAMPC_ERR_CUDA;
+  }
+  *out = h;
+  return CUDAMPC_OK;
+}
+
+int cudampc_destroy(cudampc_handle* h) {
+  if (!h) return CUDAMPC_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->warm); cudaFree(h->scratch); cudaFree(h->work); cudaFree(h->counter);
+  cudaFree(h->d_in); cudaFree(h->d_out);
+  if (h->h_in) cudaFreeHost(h->h_in);
+  if (h->h_out) cudaFreeHost(h->h_out);
+  delete h;
+  return CUDAMPC_OK;
+}
+
+int cudampc_set_params(cudampc_handle* h, const cudampc_params* params) {
+  if (!h) return CUDAMPC_ERR_INVALID;
+  Params p;
+  int rc = convert_params(params, &p, h);
+  if (rc) return rc;
+  if (p.N != h->N) return fail(h, CUDAMPC_ERR_INVALID, "%s", "horizon cannot change on an existing handle");
+  h->p = p;
+  return CUDAMPC_OK;
+}
+
+int cudampc_workspace_doubles(const cudampc_handle* h) { return h ? footprint(h->N) : 0; }
+int cudampc_problems_per_sm(const cudampc_handle* h) { return h ? h->per_sm : 0; }
+int64_t cudampc_launch_count(const cudampc_handle* h) { return h ? h->launches : 0; }
+
+int cudampc_linearize_batch(cudampc_handle* h, int batch, const double* ref_dev, double* A_dev, double* B_dev,
+                            double* c_dev, void* stream) {
+  if (!h) return CUDAMPC_ERR_INVALID;
+  if (batch < 0 || !ref_dev || !A_dev || !B_dev || !c_dev) return fail(h, CUDAMPC_ERR_INVALID, "%s", "linearize_batch: NULL pointer or negative batch");
+  if (batch == 0) return CUDAMPC_OK;
+  CU(h, cudaSetDevice(h->device));
+  const int wpb = 4;
+  int grid = (batch + wpb - 1) / wpb;
+  if (grid > h->sms * 8) grid = h->sms * 8;
+  size_t sm = (size_t)wpb * (h->N + 1) * sizeof(double);
+  mpc_linearize_kernel<<<grid, 32 * wpb, sm, (cudaStream_t)stream>>>(h->p, batch, ref_dev, A_dev, B_dev, c_dev);
+  h->launches++;
+  CU(h, cudaGetLastError());
+  return CUDAMPC_OK;
+}
+
+int cudampc_solve_batch(cudampc_handle* h, int batch, const double* x0_dev, const double* ref_dev,
+                        const double* u_prev_dev, const cudampc_settings* settings, double* u0_dev, double* Xp_dev,
+                        double* Up_dev, int32_t* status_dev, int32_t* iters_dev, double* pri_res_dev,
+                        double* dua_res_dev, int32_t* info_dev, void* stream) {
+  if (!h) return CUDAMPC_ERR_INVALID;
+  if (batch < 0 || batch > h->max_batch) return fail(h, CUDAMPC_ERR_INVALID, "%s", "solve_batch: batch out of range for this handle");
+  if (!x0_dev || !ref_dev || !u0_dev || !Xp_dev || !Up_dev || !status_dev || !iters_dev)
+    return fail(h, CUDAMPC_ERR_INVALID, "%s", "solve_batch: NULL pointer");
+  Settings s;
+  int rc = convert_settings(settings, &s, h);
+  if (rc) return rc;
+  if (batch == 0) return CUDAMPC_OK;
+  CU(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(h, cudaMemsetAsync(h->counter, 0, sizeof(int), st));
+  BatchArgs a;
+  a.x0 = x0_dev; a.ref = ref_dev; a.u_prev = u_prev_dev; a.warm = h->warm; a.scratch = h->scratch;
+  a.u0 = u0_dev; a.Xp = Xp_dev; a.Up = Up_dev; a.status = status_dev; a.iters = iters_dev;
+  a.pri = pri_res_dev; a.dua = dua_res_dev; a.info = info_dev; a.counter = h->counter; a.batch = batch;
+  if (h->use_cta) {
+    int grid = (batch + h->cta_P - 1) / h->cta_P;
+    if (grid > h->sms) grid = h->sms;
+    mpc_solve_cta_kernel<<<grid, 32 * h->cta_P, h->cta_smem, st>>>(h->p, s, a, h->cta_P, footprint(h->N), h->cta_chunk);
+  } else {
+    int grid = h->sms * h->per_sm;
+    if (grid > batch) grid = batch;
+    mpc_solve_kernel<<<grid, 32, h->smem_bytes, st>>>(h->p, s, a);
+  }
+  h->launches++;
+  CU(h, cudaGetLastError());
+  return CUDAMPC_OK;
+}
+
+int cudampc_solve_batch_host(cudampc_handle* h, int batch, const double* x0, const double* ref, const double* u_prev,
+                             const cudampc_settings* settings, double* u0, double* Xp, double* Up, int32_t* status,
+                             int32_t* iters, double* pri_res, double* dua_res, int32_t* info, void* stream) {
+  if (!h) return CUDAMPC_ERR_INVALID;
+  if (batch < 0 || batch > h->max_batch) return fail(h, CUDAMPC_ERR_INVALID, "%s", "solve_batch_host: batch out of range for this handle");
+  if (!x0 || !ref || !u0 || !Xp || !Up || !status || !iters) return fail(h, CUDAMPC_ERR_INVALID, "%s", "solve_batch_host: NULL pointer");
+  if (batch == 0) return CUDAMPC_OK;
+  CU(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = h->N;
+  const size_t B = (size_t)batch;
+  const size_t n_x0 = 4 * B, n_ref = 4 * (size_t)(N + 1) * B, n_up = 2 * B;
+  // inputs: pageable/pinned host -> pinned staging -> device (one copy)
+  memcpy(h->h_in, x0, n_x0 * sizeof(double));
+  memcpy(h->h_in + n_x0, ref, n_ref * sizeof(double));
+  if (u_prev) memcpy(h->h_in + n_x0 + n_ref, u_prev, n_up * sizeof(double));
+  else memset(h->h_in + n_x0 + n_ref, 0, n_up * sizeof(double));
+  const size_t n_in = n_x0 + n_ref + n_up;
+  CU(h, cudaMemcpyAsync(h->d_in, h->h_in, n_in * sizeof(double), cudaMemcpyHostToDevice, st));
+  // outputs, packed
+  const size_t n_u0 = 2 * B, n_xp = 4 * (size_t)(N + 1) * B, n_upo = 2 * (size_t)N * B;
+  double* d_u0 = h->d_out; double* d_xp = d_u0 + n_u0; double* d_up = d_xp + n_xp;
+  double* d_pri = d_up + n_upo; double* d_dua = d_pri + B;
+  int32_t* d_int = reinterpret_cast<int32_t*>(d_dua + B);   // status[B], iters[B], info[4B]
+  int rc = cudampc_solve_batch(h, batch, h->d_in, h->d_in + n_x0, h->d_in + n_x0 + n_ref, settings, d_u0, d_xp, d_up,
+                               d_int, d_int + B, d_pri, d_dua, d_int + 2 * B, stream);
+  if (rc) return rc;
+  const size_t n_out = n_u0 + n_xp + n_upo + 2 * B + 3 * B;   // 6 int32 per problem = 3 doubles
+  CU(h, cudaMemcpyAsync(h->h_out, h->d_out, n_out * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(h, cudaStreamSynchronize(st));
+  memcpy(u0, h->h_out, n_u0 * sizeof(double));
+  memcpy(Xp, h->h_out + n_u0, n_xp * sizeof(double));
+  memcpy(Up, h->h_out + n_u0 + n_xp, n_upo * sizeof(double));
+  const double* hp = h->h_out + n_u0 + n_xp + n_upo;
+  if (pri_res) memcpy(pri_res, hp, B * sizeof(double));
+  if (dua_res) memcpy(dua_res, hp + B, B * sizeof(double));
+  const int32_t* hi = reinterpret_cast<const int32_t*>(hp + 2 * B);
+  memcpy(status, hi, B * sizeof(int32_t));
+  memcpy(iters, hi + B, B * sizeof(int32_t));
+  if (info) memcpy(info, hi + 2 * B, 4 * B * sizeof(int32_t));
+  return CUDAMPC_OK;
+}
+
+int cudampc_rollout_batch(cudampc_handle* h, int batch, const double* ref_global_dev, const int32_t* ref_len_dev,
+                          int ref_stride, const double* state0_dev, const double* goal_dev,
+                          const cudampc_settings* settings, const cudampc_rollout_cfg* cfg, double* states_dev,
+                          double* controls_dev, int32_t* n_steps_dev, int32_t* flags_dev, int32_t* step_status_dev,
+                          int32_t* step_iters_dev, void* stream) {
+  if (!h) return CUDAMPC_ERR_INVALID;
+  if (batch < 0 || batch > h->max_batch) return fail(h, CUDAMPC_ERR_INVALID, "%s", "rollout_batch: batch out of range for this handle");
+  if (!ref_global_dev || !ref_len_dev || !state0_dev || !goal_dev || !states_dev || !n_steps_dev || !flags_dev || ref_stride < 1)
+    return fail(h, CUDAMPC_ERR_INVALID, "%s", "rollout_batch: NULL pointer or bad stride");
+  cudampc_rollout_cfg c;
+  if (cfg) c = *cfg; else cudampc_default_rollout_cfg(&c);
+  if (c.sim_steps < 1) return fail(h, CUDAMPC_ERR_INVALID, "%s", "rollout_batch: sim_steps must be >= 1");
+  Settings s;
+  int rc = convert_settings(settings, &s, h);
+  if (rc) return rc;
+  if (batch == 0) return CUDAMPC_OK;
+  CU(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(h, cudaMemsetAsync(h->counter, 0, sizeof(int), st));
+  RolloutArgs a;
+  a.ref_global = ref_global_dev; a.ref_len = ref_len_dev; a.ref_stride = ref_stride; a.state0 = state0_dev; a.goal = goal_dev;
+  a.warm = h->warm; a.scratch = h->scratch; a.work = h->work;
+  a.states = states_dev; a.controls = controls_dev; a.n_steps = n_steps_dev; a.flags = flags_dev;
+  a.step_status = step_status_dev; a.step_iters = step_iters_dev; a.counter = h->counter; a.batch = batch;
+  int grid = h->sms * h->per_sm;
+  if (grid > batch) grid = batch;
+  mpc_rollout_kernel<<<grid, 32, h->smem_bytes, st>>>(h->p, s, c, a);
+  h->launches++;
+  CU(h, cudaGetLastError());
+  return CUDAMPC_OK;
+}
+
+}  // extern "C"

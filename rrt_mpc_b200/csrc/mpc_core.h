@@ -70,10 +70,28 @@ enum {
 enum { H_X0 = 0, H_UPREV = 4, H_YI = 6, H_ACT = 10, HDR_FIXED = 10 };
 
 MPC_HD int hdr_size(int N) { return HDR_FIXED + ((N + 2 + 1) >> 1); }
-MPC_HD int nband(int N) { return 6 * N + 4; }
+MPC_HD int nband(int N) { return 6 * (N + 1); }   // terminal stage carries two dummy unknowns (identity rows)
+
+// Factor storage: one block of BLK doubles per stage (plus one padding block), 16-byte aligned so that a
+// whole block is staged with 128-bit loads:
+//   [0..14]  in-stage strictly lower L_k[j][jp], jp < j          -> IA(j,jp)
+//   [15..20] diagonal (before factorisation) / 1/D (after)       -> ID(j)
+//   [22..42] cross block L[(k,j)][(k-1,jp)], jp >= j (band = 6)  -> IC(j,jp)
+// Both sweeps of stage k need exactly: in-stage part of block k plus one cross part (forward: block k+1,
+// backward: block k).
+enum { BLK = 44 };
+#define MPC_IA(j, jp) ((j) * ((j) - 1) / 2 + (jp))
+#define MPC_ID(j) (15 + (j))
+#define MPC_IC(j, jp) (22 + 6 * (j) - (j) * ((j) - 1) / 2 + ((jp) - (j)))
+
+MPC_HD int band_offset(int N) {           // even => 16-byte aligned blocks
+  int o = hdr_size(N) + (N + 1) * SR + 7 * (N + 3);
+  return (o + 1) & ~1;
+}
 MPC_HD int footprint(int N) {
-  int f = hdr_size(N) + (N + 1) * (SR + 7) + 7 * nband(N);
-  return f | 1;  // odd => conflict-free when lanes stride over problems
+  int f = band_offset(N) + BLK * (N + 2);
+  while ((f & 3) != 2) ++f;               // F = 2 (mod 4): conflict-free 128-bit loads when lanes stride over problems
+  return f;
 }
 // warm-start state kept in HBM between calls: per stage xu(6) s(5) v(15) ye(4), + yi(4) + rho
 MPC_HD int warm_size(int N) { return 30 * (N + 1) + 5; }
@@ -84,9 +102,11 @@ struct View {
   MPC_HD double* hdr() const { return base; }
   MPC_HD int* act() const { return reinterpret_cast<int*>(base + H_ACT); }  // [N+1] stage masks + [N+1]=init rows
   MPC_HD double* rec(int k) const { return base + hdr_size(N) + k * SR; }
-  MPC_HD double* bx(int k) const { return base + hdr_size(N) + (N + 1) * SR + 7 * k; }
-  MPC_HD double* band(int i) const { return base + hdr_size(N) + (N + 1) * (SR + 7) + 7 * i; }
+  MPC_HD double* bx(int k) const { return base + hdr_size(N) + (N + 1) * SR + 7 * (k + 1); }       // k = -1 .. N+1
+  MPC_HD double* blk(int k) const { return base + band_offset(N) + BLK * k; }                      // k = 0 .. N+1
 };
+
+struct alignas(16) D2 { double x, y; };   // 128-bit shared-memory access (blocks are 16-byte aligned)
 
 MPC_HD double clipd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
 MPC_HD double dmax(double a, double b) { return a > b ? a : b; }
@@ -235,22 +255,48 @@ struct BxXV { View w; MPC_HD double operator()(int k, int j) const { return w.bx
 // ----------------------------------------------------------------------------------------------
 // Problem setup
 // ----------------------------------------------------------------------------------------------
-// stage k: linearise + cost vector from the (already unwrapped, stored in R_Q slots temporarily? no:)
-// ref rows are read from global memory `ref` ([N+1][4], yaw replaced by unwrapped yaw in `uyaw`).
-MPC_HD void setup_stage(const View& w, const Params& p, int k, const double* ref, const double* uyaw) {
+// Reference window accessor: row k of the window is row min(start+k, len-1) of `base` ([len][4]), i.e. the
+// tail padding of control_stage.py:101-105 / ref_builder.py:19-21; vscale = 0.6 in the relaxation retry
+// (control_stage.py:46-47), else 1.
+struct RefWin {
+  const double* base; int start, len; double vscale;
+  MPC_HD const double* row(int k) const { int i = start + k; if (i > len - 1) i = len - 1; return base + 4 * (size_t)i; }
+  MPC_HD double v(int k) const { double x = row(k)[3]; return vscale == 1.0 ? x : x * vscale; }
+};
+// unwrap the window's yaw column (sequential)
+MPC_HD void unwrap_window(const RefWin& rw, int count, double* out) {
+  const double PI = 3.141592653589793;
+  double cum = 0.0, prev = rw.row(0)[2];
+  out[0] = prev;
+  for (int k = 1; k < count; ++k) {
+    double cur = rw.row(k)[2];
+    double dd = cur - prev;
+    double ddmod = np_mod(dd + PI, 2.0 * PI) - PI;
+    if (ddmod == -PI && dd > 0.0) ddmod = PI;
+    double corr = ddmod - dd;
+    if (fabs(dd) < PI) corr = 0.0;
+    cum += corr;
+    out[k] = cur + cum;
+    prev = cur;
+  }
+}
+// stage k: linearise (at window row max(k-1,0), unwrapped yaw) + linear cost of x_k
+MPC_HD void setup_stage(const View& w, const Params& p, int k, const RefWin& rw, const double* uyaw) {
   const int N = w.N;
   double* rc = w.rec(k);
   if (k < N) {
     int kl = k > 0 ? k - 1 : 0;
-    linearize_point(p, ref[4 * kl + 0], ref[4 * kl + 1], uyaw[kl], ref[4 * kl + 3], rc + R_LIN);
+    const double* r = rw.row(kl);
+    linearize_point(p, r[0], r[1], uyaw[kl], rw.v(kl), rc + R_LIN);
   } else {
     for (int j = 0; j < 7; ++j) rc[R_LIN + j] = 0.0;
   }
   const double* qd = k < N ? p.q : p.qn;
-  rc[R_Q + 0] = -2.0 * qd[0] * ref[4 * k + 0];
-  rc[R_Q + 1] = -2.0 * qd[1] * ref[4 * k + 1];
+  const double* r = rw.row(k);
+  rc[R_Q + 0] = -2.0 * qd[0] * r[0];
+  rc[R_Q + 1] = -2.0 * qd[1] * r[1];
   rc[R_Q + 2] = -2.0 * qd[2] * uyaw[k];
-  rc[R_Q + 3] = -2.0 * qd[3] * ref[4 * k + 3];
+  rc[R_Q + 3] = -2.0 * qd[3] * rw.v(k);
 }
 
 // cold start: x = 0, y = 0, z = clip(0, l, u)  (v = z for inequality rows)
@@ -271,7 +317,7 @@ MPC_HD void cold_start_stage(const View& w, const Params& p, int k) {
 
 // ----------------------------------------------------------------------------------------------
 // Band assembly: rows 6k..6k+5 of  M = P + reg I + sum_rows w_i a_i a_i' + sum_groups kappa g g'
-//   band(i)[d-1] = M[i][i-d], d = 1..6 ; band(i)[6] = M[i][i]
+//   written in the stage-blocked layout (MPC_IA / MPC_ID / MPC_IC)
 // ----------------------------------------------------------------------------------------------
 MPC_HD int act_group_bits(const View& w, int k, int g) { return (w.act()[k] >> (3 * g)) & 7; }
 MPC_HD int act_dyn_bit(const View& w, int k, int r) { return (w.act()[k] >> (15 + r)) & 1; }
@@ -330,90 +376,201 @@ MPC_HD void assemble_stage(const View& w, const Params& p, const Mode& m, int k)
       }
     }
   }
-  for (int j = 0; j < nj; ++j) {
-    double* b = w.band(6 * k + j);
-    for (int d = 1; d <= 6; ++d) {
-      double val;
-      if (d <= j) val = D[j][j - d];
-      else val = (k > 0) ? E[j][j + 6 - d] : 0.0;
-      b[d - 1] = val;
+  double* b = w.blk(k);
+  for (int j = 0; j < 6; ++j) {
+    if (j < nj) {
+      for (int jp = 0; jp < j; ++jp) b[MPC_IA(j, jp)] = D[j][jp];
+      b[MPC_ID(j)] = D[j][j];
+      for (int jp = j; jp < 6; ++jp) b[MPC_IC(j, jp)] = (k > 0) ? E[j][jp] : 0.0;
+    } else {            // dummy unknowns of the terminal stage
+      for (int jp = 0; jp < j; ++jp) b[MPC_IA(j, jp)] = 0.0;
+      b[MPC_ID(j)] = 1.0;
+      for (int jp = j; jp < 6; ++jp) b[MPC_IC(j, jp)] = 0.0;
     }
-    b[6] = D[j][j];
   }
+  b[21] = 0.0; b[43] = 0.0;
 }
 
 // ----------------------------------------------------------------------------------------------
-// Banded LDL' (unit lower L, half-bandwidth 6), in place, sequential.
-//   after: band(i)[d-1] = L[i][i-d], band(i)[6] = 1/D[i]
+// Banded LDL' (unit lower L, half-bandwidth 6) as a right-looking block algorithm over stages, everything
+// of one stage staged in registers: factor the 6x6 in-stage block, form the cross block of the next stage,
+// apply its Schur complement to the next stage's in-stage block.  Sequential over stages [k0, k1).
+//   after: IA = L in-stage, ID = 1/D, IC = L cross
 // ----------------------------------------------------------------------------------------------
-MPC_HD void factor_band(const View& w) {
-  const int n = nband(w.N);
-  for (int i = 0; i < n; ++i) {
-    double* bi = w.band(i);
-    double W[6];                       // W[d-1] = L[i][i-d] * D[i-d]
-    double dii = bi[6];
-    const int dmax_ = i < 6 ? i : 6;
-    for (int d = dmax_; d >= 1; --d) {  // column j = i-d, increasing j
-      const int j = i - d;
-      const double* bj = w.band(j);
-      double s = bi[d - 1];
-      // sum over t = max(i-6, j-6, 0) .. j-1 : W_i[t] * L[j][t] ;  t = i - e, e = d+1..dmax_ ; L[j][t] = bj[(j-t)-1] = bj[e-d-1]
-      for (int e = d + 1; e <= dmax_; ++e) {
-        if (e - d <= 6) s -= W[e - 1] * bj[e - d - 1];
+MPC_HD void factor_stages(const View& w, int k0, int k1) {
+  const int N = w.N;
+  for (int k = k0; k < k1; ++k) {
+    double* __restrict__ Bk = w.blk(k);
+    double S[6][6], Lm[6][6], dinv[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+#pragma unroll
+      for (int jp = 0; jp < j; ++jp) S[j][jp] = Bk[MPC_IA(j, jp)];
+      S[j][j] = Bk[MPC_ID(j)];
+    }
+#pragma unroll
+    for (int jp = 0; jp < 6; ++jp) {
+      dinv[jp] = 1.0 / S[jp][jp];
+#pragma unroll
+      for (int j = jp + 1; j < 6; ++j) {
+        const double l = S[j][jp] * dinv[jp];
+        Lm[j][jp] = l;
+#pragma unroll
+        for (int j2 = jp + 1; j2 <= j; ++j2) S[j][j2] = fma(-l, S[j2][jp], S[j][j2]);   // S[j2][jp] still unscaled
       }
-      W[d - 1] = s;
-      double lij = s * bj[6];          // bj[6] already holds 1/D[j]
-      bi[d - 1] = lij;
-      dii -= s * lij;
     }
-    for (int d = dmax_ + 1; d <= 6; ++d) bi[d - 1] = 0.0;
-    bi[6] = 1.0 / dii;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+#pragma unroll
+      for (int jp = 0; jp < j; ++jp) Bk[MPC_IA(j, jp)] = Lm[j][jp];
+      Bk[MPC_ID(j)] = dinv[j];
+    }
+    if (k < N) {
+      double* __restrict__ Bn = w.blk(k + 1);
+      double Wc[6][6], Cl[6][6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+#pragma unroll
+        for (int jp = j; jp < 6; ++jp) {
+          double sv = Bn[MPC_IC(j, jp)];
+#pragma unroll
+          for (int t = j; t < jp; ++t) sv = fma(-Wc[j][t], Lm[jp][t], sv);
+          Wc[j][jp] = sv;
+          Cl[j][jp] = sv * dinv[jp];
+        }
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+#pragma unroll
+        for (int jp = j; jp < 6; ++jp) Bn[MPC_IC(j, jp)] = Cl[j][jp];
+#pragma unroll
+        for (int j2 = 0; j2 <= j; ++j2) {
+          double acc = 0.0;
+#pragma unroll
+          for (int t = j; t < 6; ++t) acc = fma(Wc[j][t], Cl[j2][t], acc);
+          if (j2 < j) Bn[MPC_IA(j, j2)] -= acc; else Bn[MPC_ID(j)] -= acc;
+        }
+      }
+    }
   }
 }
+MPC_HD void factor_band(const View& w) { factor_stages(w, 0, w.N + 1); }
 
-// Solve L D L' x = b in place on bx (stride 7 per stage), sequential.
+// Solve L D L' x = b in place on bx (stride 7 per stage), sequential, in column-oriented (axpy) form:
+// as soon as a pivot value is known it is pushed into the accumulators of the six rows that depend on
+// it, so only ONE fma separates consecutive pivots and the other five issue in its shadow (the SM issues
+// in order; a dot-product formulation would serialise six dependent fmas per row).  The factor block of a
+// stage is staged in registers before any arithmetic so that the shared-memory latency is paid once per
+// stage, not once per fma.
+struct ChainRegs { double la[22], lc[22], nb[6]; };
+
+// stage the factor block(s) and the next right-hand side of one forward / backward stage in registers
+MPC_HD void chain_load_fwd(const View& w, int k, ChainRegs& r) {
+  const D2* __restrict__ pa = reinterpret_cast<const D2*>(w.blk(k));
+  const D2* __restrict__ pc = reinterpret_cast<const D2*>(w.blk(k + 1) + 22);
+#pragma unroll
+  for (int i = 0; i < 11; ++i) { D2 u = pa[i], v = pc[i]; r.la[2 * i] = u.x; r.la[2 * i + 1] = u.y; r.lc[2 * i] = v.x; r.lc[2 * i + 1] = v.y; }
+  const double* bn = w.bx(k + 1);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) r.nb[j] = bn[j];
+}
+MPC_HD void chain_load_bwd(const View& w, int k, ChainRegs& r) {
+  const D2* __restrict__ pa = reinterpret_cast<const D2*>(w.blk(k));
+#pragma unroll
+  for (int i = 0; i < 11; ++i) { D2 u = pa[i], v = pa[11 + i]; r.la[2 * i] = u.x; r.la[2 * i + 1] = u.y; r.lc[2 * i] = v.x; r.lc[2 * i + 1] = v.y; }
+  const double* bp = w.bx(k - 1);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) r.nb[j] = bp[j];
+}
+MPC_HD void chain_math_fwd(const ChainRegs& r, double* a, double* out) {
+  double nx[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) nx[j] = r.nb[j];
+#pragma unroll
+  for (int jp = 0; jp < 6; ++jp) {
+    const double wv = a[jp];
+    out[jp] = wv * r.la[MPC_ID(jp)];
+#pragma unroll
+    for (int j = jp + 1; j < 6; ++j) a[j] = fma(-r.la[MPC_IA(j, jp)], wv, a[j]);
+#pragma unroll
+    for (int j = 0; j <= jp; ++j) nx[j] = fma(-r.lc[MPC_IC(j, jp) - 22], wv, nx[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) a[j] = nx[j];
+}
+MPC_HD void chain_math_bwd(const ChainRegs& r, double* a, double* out) {
+  double nx[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) nx[j] = r.nb[j];
+#pragma unroll
+  for (int jp = 5; jp >= 0; --jp) {
+    const double xv = a[jp];
+    out[jp] = xv;
+#pragma unroll
+    for (int j = jp - 1; j >= 0; --j) a[j] = fma(-r.la[MPC_IA(jp, j)], xv, a[j]);
+#pragma unroll
+    for (int j = 5; j >= jp; --j) nx[j] = fma(-r.lc[MPC_IC(jp, j) - 22], xv, nx[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) a[j] = nx[j];
+}
+
+// Software-pipelined by hand (two register sets, loop unrolled by two): the loads of stage k+1 are issued
+// BEFORE the arithmetic and the stores of stage k, so that their latency hides under ~40 DFMAs; the
+// compiler cannot do this itself because it must assume the stores alias the next loads.
 MPC_HD void chain_solve(const View& w) {
   const int N = w.N;
-  const int n = nband(N);
-  // forward: w_i = b_i - sum_d L[i][i-d] w_{i-d}; then scale by 1/D
-  double h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, h5 = 0;   // h{d-1} = w_{i-d}
+  double a[6], out[6];
+  ChainRegs r0, r1;
+  // ---- forward: w = L^{-1} b, stored scaled by D^{-1} ----
   {
-    int i = 0;
-    for (int k = 0; k <= N; ++k) {
-      double* b = w.bx(k);
-      const int nj = k < N ? 6 : 4;
-      for (int j = 0; j < nj; ++j, ++i) {
-        const double* l = w.band(i);
-        double acc = b[j];
-        acc = fma(-l[5], h5, acc); acc = fma(-l[4], h4, acc); acc = fma(-l[3], h3, acc);
-        acc = fma(-l[2], h2, acc); acc = fma(-l[1], h1, acc); acc = fma(-l[0], h0, acc);
-        b[j] = acc * l[6];
-        h5 = h4; h4 = h3; h3 = h2; h2 = h1; h1 = h0; h0 = acc;
-      }
+    const double* b0 = w.bx(0);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) a[j] = b0[j];
+    chain_load_fwd(w, 0, r0);
+    int k = 0;
+    for (; k + 1 <= N; k += 2) {
+      chain_load_fwd(w, k + 1, r1);
+      chain_math_fwd(r0, a, out);
+      { double* bk = w.bx(k);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) bk[j] = out[j]; }
+      if (k + 2 <= N) chain_load_fwd(w, k + 2, r0);
+      chain_math_fwd(r1, a, out);
+      { double* bk = w.bx(k + 1);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) bk[j] = out[j]; }
+    }
+    if (k <= N) {
+      chain_math_fwd(r0, a, out);
+      double* bk = w.bx(k);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) bk[j] = out[j];
     }
   }
-  // backward: x_i = w_i - sum_d L[i+d][i] x_{i+d}
-  h0 = h1 = h2 = h3 = h4 = h5 = 0;                           // h{d-1} = x_{i+d}
+  // ---- backward: x = L^{-T} (D^{-1} w) ----
   {
-    int i = n - 1;
-    for (int k = N; k >= 0; --k) {
-      double* b = w.bx(k);
-      const int nj = k < N ? 6 : 4;
-      for (int j = nj - 1; j >= 0; --j, --i) {
-        double acc = b[j];
-        // L[i+d][i] = band(i+d)[d-1]; rows beyond n-1 contribute 0 (h = 0)
-        const double* l = w.band(i);
-        double c5 = (i + 6 < n) ? l[7 * 6 + 5] : 0.0;
-        double c4 = (i + 5 < n) ? l[7 * 5 + 4] : 0.0;
-        double c3 = (i + 4 < n) ? l[7 * 4 + 3] : 0.0;
-        double c2 = (i + 3 < n) ? l[7 * 3 + 2] : 0.0;
-        double c1 = (i + 2 < n) ? l[7 * 2 + 1] : 0.0;
-        double c0 = (i + 1 < n) ? l[7 * 1 + 0] : 0.0;
-        acc = fma(-c5, h5, acc); acc = fma(-c4, h4, acc); acc = fma(-c3, h3, acc);
-        acc = fma(-c2, h2, acc); acc = fma(-c1, h1, acc); acc = fma(-c0, h0, acc);
-        b[j] = acc;
-        h5 = h4; h4 = h3; h3 = h2; h2 = h1; h1 = h0; h0 = acc;
-      }
+    const double* bN = w.bx(N);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) a[j] = bN[j];
+    chain_load_bwd(w, N, r0);
+    int k = N;
+    for (; k - 1 >= 0; k -= 2) {
+      chain_load_bwd(w, k - 1, r1);
+      chain_math_bwd(r0, a, out);
+      { double* bk = w.bx(k);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) bk[j] = out[j]; }
+      if (k - 2 >= 0) chain_load_bwd(w, k - 2, r0);
+      chain_math_bwd(r1, a, out);
+      { double* bk = w.bx(k - 1);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) bk[j] = out[j]; }
+    }
+    if (k >= 0) {
+      chain_math_bwd(r0, a, out);
+      double* bk = w.bx(k);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) bk[j] = out[j];
     }
   }
 }
@@ -501,6 +658,7 @@ MPC_HD void admm_rhs_stage(const View& w, const Params& p, const Settings& s, do
     double qj = j < 4 ? rc[R_Q + j] : 0.0;
     b[j] = s.sigma * rc[R_XU + j] - qj + out[j];
   }
+  for (int j = nj; j < 6; ++j) b[j] = 0.0;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -614,8 +772,12 @@ MPC_HD int polish_activity_stage(const View& w, const Params& p, double rho, int
         y = rho * (v - z);
         a = (r == 0) ? (bhi[r] - z < y) : (z - blo[r] < -y);
       } else {
+        // primal-dual active set on the polished pair; rows that are active with a zero multiplier
+        // (|margin| below round-off of the regularised solve) keep their previous bit
         y = v;
-        a = (r == 0) ? (bhi[r] - ax[r] < y) : (ax[r] - blo[r] < -y);
+        double margin = (r == 0) ? (y - (bhi[r] - ax[r])) : (-y - (ax[r] - blo[r]));
+        a = margin > 0.0;
+        if (fabs(margin) <= 1e-7) a = (w.act()[k] >> (3 * g + r)) & 1;
       }
       rc[R_V + 3 * g + r] = a ? y : 0.0;
       bits |= a << (3 * g + r);
@@ -690,6 +852,7 @@ MPC_HD void polish_rhs_stage(const View& w, const Params& p, const Mode& m, int 
     double qj = j < 4 ? rc[R_Q + j] : 0.0;
     b[j] = -qj - pd * rc[R_XU + j] + out[j];
   }
+  for (int j = nj; j < 6; ++j) b[j] = 0.0;
 }
 // S3a(k): ds and dy from the banded correction; y += dy (row-owned); ds left in R_ST
 MPC_HD void polish_dual_stage(const View& w, const Params& p, const Mode& m, int k) {

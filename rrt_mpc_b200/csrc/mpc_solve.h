@@ -11,7 +11,7 @@ namespace mpc {
 
 struct ProblemIO {
   const double* x0;      // [4]
-  const double* ref;     // [N+1][4] time-major (mpc_controller.py:42)
+  RefWin ref;            // window rows [x,y,yaw,v], time-major (mpc_controller.py:42)
   const double* u_prev;  // [2]
   double* warm;          // HBM slot, warm_size(N) doubles (ADMM iterate; also polish back-up)
   double* scratch;       // HBM slot, warm_size(N) doubles (polished-solution back-up between passes)
@@ -48,12 +48,13 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
   int n_rho = 0, n_fac = 0, n_solve = 0, n_pol = 0;
 
   // ---- load + linearise ------------------------------------------------------------------
+  ex.tag(0);
   ex.single([&]() {
     double* h = w.hdr();
     for (int i = 0; i < 4; ++i) h[H_X0 + i] = io.x0[i];
     for (int i = 0; i < 2; ++i) h[H_UPREV + i] = io.u_prev ? io.u_prev[i] : 0.0;
     for (int i = 0; i < N + 2; ++i) w.act()[i] = 0;
-    unwrap_yaw(io.ref + 2, 4, NS, w.bx(0), 1);           // scratch: bx area holds the unwrapped yaw column
+    unwrap_window(io.ref, NS, w.bx(0));                   // scratch: bx area holds the unwrapped yaw column
   });
   ex.stages(NS, [&](int k) { setup_stage(w, p, k, io.ref, w.bx(0)); });
 
@@ -78,12 +79,12 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
   Residuals res; res.pri = res.dua = 1e300; res.eps_p = res.eps_d = 0.0; res.sp = res.sd = 0.0; res.nz = res.nq = 0.0;
   while (it < s.max_iter) {
     ++it;
-    ex.solve(w); ++n_solve;
-    ex.stages(NS, [&](int k) { admm_update_stage(w, p, s, rho, k); admm_relax_x_stage(w, s, k); });
+    ex.tag(1); ex.solve(w); ++n_solve;
+    ex.tag(2); ex.stages(NS, [&](int k) { admm_update_stage(w, p, s, rho, k); admm_relax_x_stage(w, s, k); });
     const bool check = (s.check_termination > 0) && (it % s.check_termination == 0);
     const bool adapt = s.adaptive_rho && (s.adaptive_rho_interval > 0) && (it % s.adaptive_rho_interval == 0);
     if (check || adapt) {
-      res = compute_residuals(ex, w, p, s, rho, 0);
+      ex.tag(3); res = compute_residuals(ex, w, p, s, rho, 0);
       if (check && res.pri <= res.eps_p && res.dua <= res.eps_d) { status = STATUS_SOLVED; break; }
       if (adapt) {
         double rho_new = rho * sqrt(res.sp / (res.sd + 1e-10));
@@ -92,13 +93,14 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
           ex.stages(NS, [&](int k) { rescale_v_stage(w, p, rho, rho_new, k); });
           rho = rho_new; ++n_rho;
           mode = admm_mode(rho, s);
-          ex.stages(NS, [&](int k) { assemble_stage(w, p, mode, k); });
-          ex.factor(w); ++n_fac;
+          ex.tag(4); ex.stages(NS, [&](int k) { assemble_stage(w, p, mode, k); });
+          ex.tag(5); ex.factor(w); ++n_fac;
         }
       }
     }
-    ex.stages(NS, [&](int k) { admm_rhs_stage(w, p, s, rho, k); });
+    ex.tag(6); ex.stages(NS, [&](int k) { admm_rhs_stage(w, p, s, rho, k); });
   }
+  ex.tag(7);
   if (status != STATUS_SOLVED) {
     res = compute_residuals(ex, w, p, s, rho, 0);
     if (res.pri <= res.eps_p && res.dua <= res.eps_d) status = STATUS_SOLVED;

@@ -1,0 +1,269 @@
+"""Drop-in ``MPCController`` backed by libcudampc.so (hand-written sm_100a CUDA, no CPU path).
+
+Same names, arguments and failure behaviour as /root/reference/src/control/mpc_controller.py:17-145:
+
+* ``MPCParameters``  — same fields and defaults (mpc_controller.py:17-30);
+* ``MPCController(params).solve(x0, ref_traj, *, u_init=None, u_prev=None)`` returns
+  ``(u0 (2,), Xp (4,N+1), Up (2,N))`` or ``(None, None, None)`` when the solver status is not
+  optimal / optimal_inaccurate (mpc_controller.py:137-141); inputs are not mutated; ``u_init`` is
+  accepted and ignored exactly as upstream (mpc_controller.py:50-51 computes it and never uses it);
+* new: ``solve_batch`` (thousands of independent problems per launch), ``linearize_batch`` and solver
+  settings as constructor arguments (upstream hard-codes them, mpc_controller.py:121-131).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+from dataclasses import dataclass, field
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+
+LOG = logging.getLogger(__name__)
+
+STATUS_SOLVED = 1
+STATUS_SOLVED_INACCURATE = 2
+STATUS_MAX_ITER = -2
+_OK = (STATUS_SOLVED, STATUS_SOLVED_INACCURATE)
+
+
+@dataclass
+class MPCParameters:
+    wheelbase_px: float
+    dt: float
+    horizon: int
+    q: np.ndarray
+    r: np.ndarray
+    q_terminal: np.ndarray
+    u_bounds: Tuple[Tuple[float, float], Tuple[float, float]]
+    v_bounds: Tuple[float, float]
+    du_bounds: Tuple[Tuple[float, float], Tuple[float, float]]
+    slack_velocity: float = 1e3
+    slack_input: float = 5e2
+    slack_rate: float = 5e2
+
+
+@dataclass
+class SolverSettings:
+    """OSQP-style settings; defaults are what the reference passes (mpc_controller.py:121-131)."""
+    eps_abs: float = 1e-3
+    eps_rel: float = 1e-3
+    max_iter: int = 60000
+    polish: bool = True
+    polish_passes: int = 1        # 1 = OSQP's single polish; >1 re-identifies the active set (used for 1e-5 parity)
+    adaptive_rho: bool = True
+    rho: float = 0.1
+    alpha: float = 1.6
+    sigma: float = 1e-6
+    check_termination: int = 25
+    adaptive_rho_interval: int = 50
+    adaptive_rho_tolerance: float = 5.0
+    delta: float = 1e-6
+    polish_refine_iter: int = 3
+    warm_start: bool = False      # upstream's warm_start=True is a no-op (a new Problem per call)
+
+    def to_c(self) -> _lib.Settings:
+        lib = _lib.load()
+        s = _lib.Settings()
+        lib.cudampc_default_settings(C.byref(s))
+        s.eps_abs, s.eps_rel, s.max_iter = self.eps_abs, self.eps_rel, int(self.max_iter)
+        s.polish_passes = int(self.polish_passes) if self.polish else 0
+        s.adaptive_rho, s.rho, s.alpha, s.sigma = int(self.adaptive_rho), self.rho, self.alpha, self.sigma
+        s.check_termination, s.adaptive_rho_interval = int(self.check_termination), int(self.adaptive_rho_interval)
+        s.adaptive_rho_tolerance, s.delta = self.adaptive_rho_tolerance, self.delta
+        s.polish_refine_iter, s.warm_start = int(self.polish_refine_iter), int(self.warm_start)
+        return s
+
+
+def params_to_c(p: MPCParameters) -> _lib.Params:
+    c = _lib.Params()
+    c.wheelbase_px, c.dt, c.horizon = float(p.wheelbase_px), float(p.dt), int(p.horizon)
+    c.q[:] = np.asarray(p.q, dtype=float).reshape(16).tolist()
+    c.r[:] = np.asarray(p.r, dtype=float).reshape(4).tolist()
+    c.q_terminal[:] = np.asarray(p.q_terminal, dtype=float).reshape(16).tolist()
+    c.u_bounds[:] = [p.u_bounds[0][0], p.u_bounds[0][1], p.u_bounds[1][0], p.u_bounds[1][1]]
+    c.v_bounds[:] = [p.v_bounds[0], p.v_bounds[1]]
+    c.du_bounds[:] = [p.du_bounds[0][0], p.du_bounds[0][1], p.du_bounds[1][0], p.du_bounds[1][1]]
+    c.slack_velocity, c.slack_input, c.slack_rate = float(p.slack_velocity), float(p.slack_input), float(p.slack_rate)
+    return c
+
+
+@dataclass
+class BatchResult:
+    u0: object          # (B,2)
+    Xp: object          # (B,4,N+1)
+    Up: object          # (B,2,N)
+    status: object      # (B,) int32, OSQP codes
+    iters: object       # (B,) int32
+    pri_res: object = None
+    dua_res: object = None
+    info: object = None  # (B,4) int32: rho updates, factorisations, accepted polish passes, triangular solves
+
+    def __iter__(self):  # (u0, Xp, Up, status, iters) unpacking as in SURVEY §8b
+        return iter((self.u0, self.Xp, self.Up, self.status, self.iters))
+
+
+class _Handle:
+    """Owns a cudampc_handle (one per (params, capacity, device))."""
+
+    def __init__(self, params: MPCParameters, max_batch: int, device: int):
+        self.lib = _lib.load()
+        self.ptr = C.c_void_p()
+        cpar = params_to_c(params)
+        rc = self.lib.cudampc_create(C.byref(cpar), int(max_batch), int(device), C.byref(self.ptr))
+        if rc != 0:
+            msg = self.lib.cudampc_last_error(None)
+            raise RuntimeError(f"cudampc_create failed (code {rc}): {msg.decode() if msg else ''}")
+        self.max_batch, self.device, self.horizon = int(max_batch), int(device), int(params.horizon)
+
+    def close(self):
+        if getattr(self, "ptr", None) and self.ptr.value:
+            self.lib.cudampc_destroy(self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _is_torch_cuda(x) -> bool:
+    return hasattr(x, "is_cuda") and bool(x.is_cuda)
+
+
+class MPCController:
+    """Quadratic-cost MPC controller with soft bounds and rate limits (batched, GPU)."""
+
+    def __init__(self, params: MPCParameters, settings: Optional[SolverSettings] = None, *, device: int = 0,
+                 max_batch: int = 1) -> None:
+        self._params = params
+        self.settings = settings or SolverSettings()
+        self._device = device
+        self._capacity = max(1, int(max_batch))
+        self._h: Optional[_Handle] = None
+
+    # -- plumbing -------------------------------------------------------------------------------
+    def _handle(self, batch: int) -> _Handle:
+        if self._h is None or batch > self._h.max_batch:
+            if self._h is not None:
+                self._h.close()
+            self._capacity = max(self._capacity, batch)
+            self._h = _Handle(self._params, self._capacity, self._device)
+        return self._h
+
+    @property
+    def params(self) -> MPCParameters:
+        return self._params
+
+    def close(self) -> None:
+        if self._h is not None:
+            self._h.close()
+            self._h = None
+
+    def launch_count(self) -> int:
+        return int(self._h.lib.cudampc_launch_count(self._h.ptr)) if self._h else 0
+
+    def problems_per_sm(self) -> int:
+        h = self._handle(1)
+        return int(h.lib.cudampc_problems_per_sm(h.ptr))
+
+    def workspace_doubles(self) -> int:
+        h = self._handle(1)
+        return int(h.lib.cudampc_workspace_doubles(h.ptr))
+
+    # -- reference signature --------------------------------------------------------------------
+    def solve(self, x0, ref_traj, *, u_init=None, u_prev=None):
+        N = self._params.horizon
+        x0 = np.ascontiguousarray(x0, dtype=float).reshape(1, 4)
+        ref = np.ascontiguousarray(np.asarray(ref_traj, dtype=float)[: N + 1]).reshape(1, N + 1, 4)
+        up = None if u_prev is None else np.ascontiguousarray(u_prev, dtype=float).reshape(1, 2)
+        res = self.solve_batch(x0, ref, u_prev=up)
+        status = int(res.status[0])
+        if status not in _OK:                      # mpc_controller.py:137-139
+            LOG.warning("MPC solve returned status %s", status)
+            return None, None, None
+        return res.u0[0].copy(), res.Xp[0].copy(), res.Up[0].copy()
+
+    # -- batched entry points -------------------------------------------------------------------
+    def solve_batch(self, x0, ref, *, u_prev=None, settings: Optional[SolverSettings] = None, stream=None) -> BatchResult:
+        """``x0 (B,4)``, ``ref (B,N+1,4)``, ``u_prev (B,2)|None`` as NumPy arrays (host path: pinned staging,
+        H2D, solve, D2H) or as torch CUDA fp64 tensors (device path: asynchronous on the current stream)."""
+        s = (settings or self.settings).to_c()
+        N = self._params.horizon
+        if _is_torch_cuda(x0):
+            return self._solve_batch_device(x0, ref, u_prev, s, stream)
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        ref = np.ascontiguousarray(ref, dtype=np.float64)
+        B = x0.shape[0]
+        if x0.shape != (B, 4) or ref.shape != (B, N + 1, 4):
+            raise ValueError(f"expected x0 (B,4) and ref (B,{N + 1},4); got {x0.shape} and {ref.shape}")
+        up = None
+        if u_prev is not None:
+            up = np.ascontiguousarray(u_prev, dtype=np.float64)
+            if up.shape != (B, 2):
+                raise ValueError(f"expected u_prev (B,2); got {up.shape}")
+        out = BatchResult(np.empty((B, 2)), np.empty((B, 4, N + 1)), np.empty((B, 2, N)), np.empty(B, np.int32),
+                          np.empty(B, np.int32), np.empty(B), np.empty(B), np.empty((B, 4), np.int32))
+        if B == 0:
+            return out
+        h = self._handle(B)
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        rc = h.lib.cudampc_solve_batch_host(h.ptr, B, ptr(x0), ptr(ref), ptr(up), C.byref(s), ptr(out.u0), ptr(out.Xp),
+                                            ptr(out.Up), ptr(out.status), ptr(out.iters), ptr(out.pri_res),
+                                            ptr(out.dua_res), ptr(out.info), None)
+        _lib.check(h.lib, h.ptr, rc, "cudampc_solve_batch_host")
+        return out
+
+    def _solve_batch_device(self, x0, ref, u_prev, s, stream) -> BatchResult:
+        import torch
+        N = self._params.horizon
+        B = x0.shape[0]
+        for name, t, shape in (("x0", x0, (B, 4)), ("ref", ref, (B, N + 1, 4))) + ((("u_prev", u_prev, (B, 2)),) if u_prev is not None else ()):
+            if tuple(t.shape) != shape or t.dtype != torch.float64 or not t.is_contiguous() or not t.is_cuda:
+                raise ValueError(f"{name}: expected contiguous CUDA float64 tensor of shape {shape}")
+        dev = x0.device
+        out = BatchResult(torch.empty((B, 2), dtype=torch.float64, device=dev),
+                          torch.empty((B, 4, N + 1), dtype=torch.float64, device=dev),
+                          torch.empty((B, 2, N), dtype=torch.float64, device=dev),
+                          torch.empty(B, dtype=torch.int32, device=dev), torch.empty(B, dtype=torch.int32, device=dev),
+                          torch.empty(B, dtype=torch.float64, device=dev), torch.empty(B, dtype=torch.float64, device=dev),
+                          torch.empty((B, 4), dtype=torch.int32, device=dev))
+        if B == 0:
+            return out
+        if self._h is None:
+            self._device = dev.index if dev.index is not None else torch.cuda.current_device()
+        h = self._handle(B)
+        st = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        rc = h.lib.cudampc_solve_batch(h.ptr, B, p(x0), p(ref), p(u_prev), C.byref(s), p(out.u0), p(out.Xp), p(out.Up),
+                                       p(out.status), p(out.iters), p(out.pri_res), p(out.dua_res), p(out.info),
+                                       C.c_void_p(st))
+        _lib.check(h.lib, h.ptr, rc, "cudampc_solve_batch")
+        return out
+
+    def linearize_batch(self, ref):
+        """(A (B,N,4,4), B (B,N,4,2), c (B,N,4)) as ``solve`` linearises them (mpc_controller.py:59-70,108-109)."""
+        import torch
+        N = self._params.horizon
+        host = not _is_torch_cuda(ref)
+        t = torch.as_tensor(np.ascontiguousarray(ref, dtype=np.float64)).cuda(self._device) if host else ref
+        B = t.shape[0]
+        if tuple(t.shape) != (B, N + 1, 4):
+            raise ValueError(f"expected ref (B,{N + 1},4); got {tuple(t.shape)}")
+        A = torch.empty((B, N, 4, 4), dtype=torch.float64, device=t.device)
+        Bm = torch.empty((B, N, 4, 2), dtype=torch.float64, device=t.device)
+        c = torch.empty((B, N, 4), dtype=torch.float64, device=t.device)
+        h = self._handle(max(B, 1))
+        st = torch.cuda.current_stream(t.device).cuda_stream
+        rc = h.lib.cudampc_linearize_batch(h.ptr, B, C.c_void_p(t.data_ptr()), C.c_void_p(A.data_ptr()),
+                                           C.c_void_p(Bm.data_ptr()), C.c_void_p(c.data_ptr()), C.c_void_p(st))
+        _lib.check(h.lib, h.ptr, rc, "cudampc_linearize_batch")
+        if host:
+            return A.cpu().numpy(), Bm.cpu().numpy(), c.cpu().numpy()
+        return A, Bm, c
+
+
+__all__ = ["MPCParameters", "SolverSettings", "MPCController", "BatchResult"]

@@ -11,6 +11,7 @@ using namespace mpc;
 
 struct EmuExec {
   int reverse;
+  void tag(int) {}
   template <class F> void stages(int n, F f) {
     if (!reverse) for (int k = 0; k < n; ++k) f(k);
     else for (int k = n - 1; k >= 0; --k) f(k);
@@ -69,7 +70,7 @@ int emu_solve_batch(const double* par, const double* set, int N, int B, int reve
     std::fill(ws.begin(), ws.end(), 0.0);
     View w{ws.data(), N};
     ProblemIO io;
-    io.x0 = x0 + 4 * b; io.ref = ref + (size_t)4 * (N + 1) * b; io.u_prev = u_prev ? u_prev + 2 * b : nullptr;
+    io.x0 = x0 + 4 * b; io.ref = RefWin{ref + (size_t)4 * (N + 1) * b, 0, N + 1, 1.0}; io.u_prev = u_prev ? u_prev + 2 * b : nullptr;
     io.warm = warm ? warm + (size_t)warm_size(N) * b : warm_local.data();
     io.scratch = scratch.data();
     io.u0 = u0 + 2 * b; io.Xp = Xp + (size_t)4 * (N + 1) * b; io.Up = Up + (size_t)2 * N * b;

@@ -1,0 +1,24 @@
+"""Device-path timing (dev tool): python tools/gpu_perf.py N B [eps]"""
+import sys, dataclasses, os
+import numpy as np
+sys.path.insert(0, ".")
+import torch
+from rrt_mpc_b200 import MPCController, SolverSettings, MPCConfig
+from rrt_mpc_b200.synthetic import make_batch
+N, B = int(sys.argv[1]), int(sys.argv[2]); eps = float(sys.argv[3]) if len(sys.argv) > 3 else 1e-6
+par = MPCConfig(horizon=N).to_parameters(0.8)
+if N == 50: par = dataclasses.replace(par, du_bounds=((-12., 12.), (-0.02, 0.02)))
+x0, ref, up = make_batch(B, N, seed=3 if N == 50 else 2)
+ctl = MPCController(par, SolverSettings(eps_abs=eps, eps_rel=eps, polish_passes=3), max_batch=B)
+d = lambda a: torch.as_tensor(a).cuda()
+dx0, dref, dup = d(x0), d(ref), d(up)
+r = ctl.solve_batch(dx0, dref, u_prev=dup); torch.cuda.synchronize()
+best = 1e9
+for _ in range(3):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); r = ctl.solve_batch(dx0, dref, u_prev=dup); e1.record(); torch.cuda.synchronize()
+    best = min(best, e0.elapsed_time(e1))
+it = r.iters.double().mean().item()
+cyc = best * 1e-3 / (B * it) * 148 * 1.8e9
+print(f"[{os.environ.get('CUDAMPC_KERNEL','cta')}] N={N} B={B} per_sm={ctl.problems_per_sm()}: {best:.2f} ms -> {B/best*1e3:.0f} solves/s, mean iters {it:.1f}, "
+      f"{cyc:.0f} SM-cycles per problem-iteration, solved {(r.status==1).sum().item()}")
