@@ -155,6 +155,10 @@ int cudampc_workspace_doubles(const cudampc_handle* h);
 int cudampc_problems_per_sm(const cudampc_handle* h);
 int64_t cudampc_launch_count(const cudampc_handle* h);
 
+/* Measured fp64 FMA throughput of the handle's device (TFLOP/s, ~50 ms of independent DFMA chains): the
+ * roofline denominator bench.py reports against (MEASURED_PEAKS.json holds no fp64 figure). < 0 on failure. */
+double cudampc_fp64_peak_tflops(cudampc_handle* h);
+
 #ifdef __cplusplus
 }
 #endif

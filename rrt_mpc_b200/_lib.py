@@ -36,7 +36,7 @@ SYMBOLS = (
     "cudampc_version", "cudampc_default_settings", "cudampc_default_rollout_cfg", "cudampc_create",
     "cudampc_destroy", "cudampc_last_error", "cudampc_set_params", "cudampc_linearize_batch",
     "cudampc_solve_batch", "cudampc_solve_batch_host", "cudampc_rollout_batch", "cudampc_workspace_doubles",
-    "cudampc_problems_per_sm", "cudampc_launch_count",
+    "cudampc_problems_per_sm", "cudampc_launch_count", "cudampc_fp64_peak_tflops",
 )
 
 _lib = None
@@ -81,6 +81,8 @@ def load() -> C.CDLL:
     lib.cudampc_problems_per_sm.restype = C.c_int
     lib.cudampc_launch_count.argtypes = [vp]
     lib.cudampc_launch_count.restype = C.c_int64
+    lib.cudampc_fp64_peak_tflops.argtypes = [vp]
+    lib.cudampc_fp64_peak_tflops.restype = C.c_double
     _lib = lib
     return lib
 

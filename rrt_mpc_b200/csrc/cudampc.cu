@@ -331,6 +331,23 @@ __global__ void __launch_bounds__(32) mpc_rollout_kernel(Params p, Settings s, c
 }
 
 // ------------------------------------------------------------------------------------------------
+// fp64 pipe peak (roofline denominator measured on the device the solver runs on)
+// ------------------------------------------------------------------------------------------------
+__global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = threadIdx.x * 1e-3 + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fma(acc[i], a, b);
+  }
+  double sum = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += acc[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = sum;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Handle + C ABI
 // ------------------------------------------------------------------------------------------------
 struct cudampc_handle {
@@ -512,6 +529,28 @@ int cudampc_set_params(cudampc_handle* h, const cudampc_params* params) {
   if (p.N != h->N) return fail(h, CUDAMPC_ERR_INVALID, "%s", "horizon cannot change on an existing handle");
   h->p = p;
   return CUDAMPC_OK;
+}
+
+double cudampc_fp64_peak_tflops(cudampc_handle* h) {
+  if (!h) return -1.0;
+  if (cudaSetDevice(h->device) != cudaSuccess) return -1.0;
+  const int blocks = h->sms * 8, threads = 256, iters = 20000;
+  double* out = nullptr;
+  if (cudaMalloc(&out, sizeof(double) * blocks * threads) != cudaSuccess) return -1.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int r = 0; r < 6; ++r) {
+    cudaEventRecord(e0);
+    fp64_peak_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-6);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.f; break; }
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    if (r > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  if (best <= 0.f) return -1.0;
+  return 2.0 * 8 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
 }
 
 int cudampc_workspace_doubles(const cudampc_handle* h) { return h ? footprint(h->N) : 0; }

@@ -170,6 +170,10 @@ class MPCController:
         h = self._handle(1)
         return int(h.lib.cudampc_problems_per_sm(h.ptr))
 
+    def fp64_peak_tflops(self) -> float:
+        h = self._handle(1)
+        return float(h.lib.cudampc_fp64_peak_tflops(h.ptr))
+
     def workspace_doubles(self) -> int:
         h = self._handle(1)
         return int(h.lib.cudampc_workspace_doubles(h.ptr))

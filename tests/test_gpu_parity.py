@@ -1,0 +1,174 @@
+"""GPU (B200): the CUDA path, called through the C ABI (ctypes wrapper), against the oracle and the golden vectors."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, oracle_params, product_params
+
+pytestmark = pytest.mark.gpu
+TIGHT = dict(eps_abs=1e-6, eps_rel=1e-6)
+
+
+def controller(N, du=0.15, passes=3, max_batch=64, **kw):
+    from rrt_mpc_b200 import MPCController, SolverSettings
+    return MPCController(product_params(N, du), SolverSettings(polish_passes=passes, **{**TIGHT, **kw}), max_batch=max_batch)
+
+
+def test_extension_is_loaded_and_counts_launches():
+    import os
+    ctl = controller(20)
+    g = load_golden("optima.npz")
+    ctl.solve_batch(g["n20_x0"][:4], g["n20_ref"][:4], u_prev=g["n20_up"][:4])
+    assert ctl.launch_count() == 1
+    maps = open(f"/proc/{os.getpid()}/maps").read()
+    assert "libcudampc.so" in maps
+
+
+@pytest.mark.parametrize("name,N", [("n20", 20), ("n50", 50)])
+def test_linearize_batch_within_1e12_of_reference(name, N):
+    g = load_golden("linearize_window.npz")          # produced by the REAL vehicle_model.linearize
+    ctl = controller(N)
+    A, B, c = ctl.linearize_batch(g[f"{name}_ref"])
+    sa = np.abs(g[f"{name}_A"]).max()
+    assert np.abs(A - g[f"{name}_A"]).max() <= 1e-12 * sa
+    assert np.abs(B - g[f"{name}_B"]).max() <= 1e-12 * np.abs(g[f"{name}_B"]).max()
+    assert np.abs(c - g[f"{name}_c"]).max() <= 1e-12 * max(sa, np.abs(g[f"{name}_ref"][:, :, :2]).max())
+    assert np.array_equal(A[:, :, 2, 3], np.zeros_like(A[:, :, 2, 3]))       # ulin = 0 => A[2,3] = 0
+
+
+@pytest.mark.parametrize("name,N,du", [("n20", 20, 0.15), ("n50", 50, 0.02)])
+def test_u0_within_1e5_of_certified_optimum(name, N, du):
+    g = load_golden("optima.npz")
+    ctl = controller(N, du)
+    r = ctl.solve_batch(g[f"{name}_x0"], g[f"{name}_ref"], u_prev=g[f"{name}_up"])
+    assert (r.status == 1).all()
+    assert np.abs(r.u0 - g[f"{name}_u0"]).max() < 1e-5                     # the north-star bar
+    assert np.abs(r.u0 - g[f"{name}_u0"]).max() < 1e-8                     # what we actually reach
+    assert np.abs(r.Xp - g[f"{name}_X"]).max() < 1e-6 and np.abs(r.Up - g[f"{name}_U"]).max() < 1e-6
+    assert np.abs(r.Xp[:, :, 0] - g[f"{name}_x0"]).max() < 1e-9            # X_0 = x0
+
+
+@pytest.mark.parametrize("name,N,du", [("n20", 20, 0.15), ("n50", 50, 0.02)])
+def test_status_and_iterations_identical_to_oracle(name, N, du):
+    from oracle import c_oracle as CO
+    g = load_golden("optima.npz")
+    nb = 12
+    ctl = controller(N, du, passes=1)
+    r = ctl.solve_batch(g[f"{name}_x0"][:nb], g[f"{name}_ref"][:nb], u_prev=g[f"{name}_up"][:nb])
+    # mirror mode: the same ADMM on the same QP, solved through a generic sparse KKT LDL' on the CPU
+    c = CO.solve_batch(oracle_params(N, du), g[f"{name}_x0"][:nb], g[f"{name}_ref"][:nb], g[f"{name}_up"][:nb], scaling=0, z0_projected=1, **TIGHT)
+    assert np.array_equal(r.status, c["status"]) and np.array_equal(r.iters, c["iters"])
+    assert np.array_equal(r.info[:, 0], c["info"][:, 0]) and np.array_equal(r.info[:, 2], c["info"][:, 2])
+    assert np.abs(r.u0 - c["u0"]).max() < 1e-9
+    # literal OSQP defaults (Ruiz scaling 10): same status, same optimum within the bar where the oracle itself is converged
+    o = CO.solve_batch(oracle_params(N, du), g[f"{name}_x0"][:nb], g[f"{name}_ref"][:nb], g[f"{name}_up"][:nb], polish_passes=3, **TIGHT)
+    assert np.array_equal(r.status, o["status"])
+    r3 = controller(N, du, passes=3).solve_batch(g[f"{name}_x0"][:nb], g[f"{name}_ref"][:nb], u_prev=g[f"{name}_up"][:nb])
+    assert np.abs(r3.u0 - o["u0"]).max() < 1e-5
+
+
+def test_matches_host_emulation_of_the_same_source():
+    import emu_driver as E
+    g = load_golden("optima.npz")
+    ctl = controller(20)
+    r = ctl.solve_batch(g["n20_x0"][:8], g["n20_ref"][:8], u_prev=g["n20_up"][:8])
+    e = E.solve(oracle_params(20), g["n20_x0"][:8], g["n20_ref"][:8], g["n20_up"][:8], polish_passes=3, **TIGHT)
+    assert np.array_equal(r.iters, e["iters"]) and np.array_equal(r.status, e["status"])
+    assert np.abs(r.u0 - e["u0"]).max() < 1e-10 and np.abs(r.Xp - e["Xp"]).max() < 1e-9
+
+
+def test_reference_signature_single_problem():
+    """tests/test_mpc_controller.py:7-17 of the reference, verbatim semantics."""
+    from rrt_mpc_b200 import MPCConfig, MPCController
+    cfg = MPCConfig(horizon=5)
+    controller_ = MPCController(cfg.to_parameters(map_resolution=0.2))
+    x0 = np.array([0.0, 0.0, 0.0, 5.0])
+    ref = np.tile(np.array([1.0, 0.0, 0.0, 5.0]), (cfg.horizon + 1, 1))
+    ref_copy = ref.copy()
+    u0, Xp, Up = controller_.solve(x0, ref)
+    assert u0 is not None and Xp is not None and Up is not None
+    assert Xp[0, 1] > x0[0]
+    assert u0.shape == (2,) and Xp.shape == (4, 6) and Up.shape == (2, 5)
+    assert np.array_equal(ref, ref_copy)                                   # inputs are not mutated
+    g = load_golden("optima.npz")
+    assert np.abs(u0 - g["unit_u0"]).max() < 1e-5
+    u0b, _, _ = controller_.solve(x0, ref, u_init=np.ones((5, 2)), u_prev=np.zeros(2))     # u_init is dead upstream
+    assert np.array_equal(u0, u0b)
+
+
+def test_failed_solve_maps_to_none_triple():
+    """mpc_controller.py:137-139: non-optimal status -> (None, None, None)."""
+    from rrt_mpc_b200 import MPCController, SolverSettings
+    g = load_golden("optima.npz")
+    ctl = MPCController(product_params(20), SolverSettings(max_iter=5, **TIGHT))
+    assert ctl.solve(g["n20_x0"][0], g["n20_ref"][0], u_prev=g["n20_up"][0]) == (None, None, None)
+    r = ctl.solve_batch(g["n20_x0"][:3], g["n20_ref"][:3], u_prev=g["n20_up"][:3])
+    assert (r.status == -2).all() and (r.iters == 5).all()
+
+
+@pytest.mark.parametrize("B", [0, 1, 3, 31, 257])
+def test_ragged_batch_sizes_and_device_path(B):
+    import torch
+    from rrt_mpc_b200.synthetic import make_batch
+    x0, ref, up = make_batch(max(B, 1), 20, seed=7)
+    x0, ref, up = x0[:B], ref[:B], up[:B]
+    ctl = controller(20, max_batch=300)
+    r = ctl.solve_batch(x0, ref, u_prev=up)
+    assert r.u0.shape == (B, 2) and r.Xp.shape == (B, 4, 21) and r.Up.shape == (B, 2, 20)
+    if B == 0:
+        return
+    d = lambda a: torch.as_tensor(a).cuda()
+    rd = ctl.solve_batch(d(x0), d(ref), u_prev=d(up))
+    torch.cuda.synchronize()
+    assert np.array_equal(rd.status.cpu().numpy(), r.status) and np.array_equal(rd.iters.cpu().numpy(), r.iters)
+    assert np.array_equal(rd.u0.cpu().numpy(), r.u0) and np.array_equal(rd.Xp.cpu().numpy(), r.Xp)
+    assert (r.status == 1).all()
+    r0 = ctl.solve_batch(x0, ref)                                          # u_prev = None -> zeros
+    rz = ctl.solve_batch(x0, ref, u_prev=np.zeros((B, 2)))
+    assert np.array_equal(r0.u0, rz.u0)
+
+
+@pytest.mark.parametrize("N", [1, 2, 7, 33, 64])
+def test_horizon_edge_cases(N):
+    from oracle import mpc_numpy as O
+    p = oracle_params(N)
+    rng = np.random.default_rng(N)
+    ref = np.zeros((4, N + 1, 4))
+    for b in range(4):
+        yaw = 0.4 * b + np.cumsum(rng.normal(size=N + 1) * 0.05)
+        ref[b, :, 2] = yaw; ref[b, :, 3] = 12.0 + rng.normal(size=N + 1)
+        ref[b, :, 0] = 80 + np.cumsum(1.5 * np.cos(yaw)); ref[b, :, 1] = 60 + np.cumsum(1.5 * np.sin(yaw))
+    x0 = ref[:, 0] + rng.normal(size=(4, 4)) * [0.5, 0.5, 0.05, 1.0]
+    up = rng.uniform(-1, 1, size=(4, 2)) * [3.0, 0.1]
+    r = controller(N).solve_batch(x0, ref, u_prev=up)
+    assert (r.status == 1).all()
+    for b in range(4):
+        u0, X, U, _ = O.solve_kkt_newton(x0[b], ref[b], up[b], p)
+        assert np.abs(r.u0[b] - u0).max() < 1e-6 and np.abs(r.Xp[b] - X).max() < 1e-6
+
+
+def test_warm_start_same_optimum_fewer_iterations():
+    from rrt_mpc_b200 import SolverSettings
+    g = load_golden("optima.npz")
+    ctl = controller(20)
+    x0, ref, up = g["n20_x0"], g["n20_ref"], g["n20_up"]
+    cold = ctl.solve_batch(x0, ref, u_prev=up)
+    x1 = x0 + 0.01
+    hot = ctl.solve_batch(x1, ref, u_prev=up, settings=SolverSettings(polish_passes=3, warm_start=True, **TIGHT))
+    fresh = controller(20).solve_batch(x1, ref, u_prev=up)
+    assert (hot.status == 1).all() and hot.iters.sum() < 0.6 * fresh.iters.sum()
+    assert np.abs(hot.u0 - fresh.u0).max() < 1e-6
+    assert cold.iters.sum() > 0
+
+
+def test_invalid_arguments_fail_loudly():
+    ctl = controller(20)
+    with pytest.raises(ValueError):
+        ctl.solve_batch(np.zeros((2, 4)), np.zeros((2, 20, 4)))            # window one row short
+    with pytest.raises(ValueError):
+        ctl.solve_batch(np.zeros((2, 4)), np.zeros((2, 21, 4)), u_prev=np.zeros((3, 2)))
+    from rrt_mpc_b200 import MPCController
+    q = np.diag([4.0, 4.0, 0.6, 0.1]); q[0, 1] = q[1, 0] = 0.1
+    with pytest.raises(RuntimeError, match="non-diagonal"):
+        MPCController(dataclasses.replace(product_params(20), q=q)).solve(np.zeros(4), np.zeros((21, 4)))

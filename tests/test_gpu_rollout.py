@@ -1,0 +1,70 @@
+"""GPU (B200): closed loop (TrajectoryTracker.track / track_batch) against the oracle's restatement of
+control_stage.py:74-157 on the default-config scenario reproduced from the real reference modules."""
+from types import SimpleNamespace as NS
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+TIGHT = dict(eps_abs=1e-6, eps_rel=1e-6)
+
+
+def scenario():
+    d = load_golden("default_scenario.npz")
+    path = [tuple(p) for p in d["path"]]
+    return d, path
+
+
+def test_default_rollout_matches_oracle_within_1e3():
+    from oracle import c_oracle as CO, mpc_numpy as O
+    from rrt_mpc_b200 import MPCConfig, SolverSettings, TrajectoryTracker
+    from rrt_mpc_b200.control_stage import initial_state
+    d, path = scenario()
+    ora = CO.track(O.Params(horizon=15), d["ref_global"], initial_state(path, d["start"]), d["goal"], 300, polish_passes=3, **TIGHT)
+    tr = TrajectoryTracker(MPCConfig(), None, settings=SolverSettings(polish_passes=3, **TIGHT))
+    # (1) batched, device-resident loop; cold start each step like the reference (a new Problem per call)
+    res = tr.track_batch([path], [d["start"]], [d["goal"]], map_resolution=0.8, warm_start=False)
+    n = int(res.n_steps[0])
+    assert n == ora["n_steps"] and bool(res.goal_reached[0]) and not bool(res.aborted[0])
+    assert np.abs(res.states[0, :n, :2] - ora["states"][:n, :2]).max() < 1e-3          # tracked positions, full rollout
+    assert np.abs(res.controls[0, :n] - ora["controls"][:n]).max() < 1e-5             # every first control
+    assert np.isnan(res.states[0, n:]).all()
+    # (2) warm-started loop converges to the same optima
+    resw = tr.track_batch([path], [d["start"]], [d["goal"]], map_resolution=0.8, warm_start=True)
+    assert int(resw.n_steps[0]) == n
+    assert np.abs(resw.states[0, :n, :2] - ora["states"][:n, :2]).max() < 1e-3
+    assert resw.step_iters[0, 1:n].sum() < res.step_iters[0, 1:n].sum()
+    # (3) the reference signature: track(planning, maps, ...) -> TrackingResult(states=[...])
+    planning = NS(plan=NS(success=True, path=path))
+    maps = NS(start=tuple(d["start"]), goal=tuple(d["goal"]))
+    out = tr.track(planning, maps, map_resolution=0.8, visualize=False)
+    assert len(out.states) == n
+    assert np.abs(np.array(out.states)[:, :2] - ora["states"][:n, :2]).max() < 1e-3
+
+
+def test_many_perturbed_vehicles():
+    """config 4 shape in small: perturbed copies of the default path, each tracked independently on the device."""
+    from oracle import c_oracle as CO, mpc_numpy as O
+    from rrt_mpc_b200 import MPCConfig, SolverSettings, TrajectoryTracker
+    from rrt_mpc_b200.control_stage import initial_state
+    from rrt_mpc_b200.ref_builder import build_reference
+    d, path = scenario()
+    rng = np.random.default_rng(4)
+    B, T = 48, 80
+    paths, starts = [], []
+    for b in range(B):
+        pts = np.array(path) + rng.normal(size=(len(path), 2)) * 0.15
+        pts[0] = path[0]
+        paths.append([tuple(p) for p in pts]); starts.append(pts[0] + rng.normal(size=2) * 0.5)
+    goals = np.tile(d["goal"], (B, 1))
+    tr = TrajectoryTracker(MPCConfig(sim_steps=T), None, settings=SolverSettings(polish_passes=3, **TIGHT))
+    res = tr.track_batch(paths, starts, goals, map_resolution=0.8, warm_start=True)
+    assert not res.aborted.any() and res.goal_reached.mean() > 0.9
+    for b in (0, 7, 23, 47):
+        rg = build_reference(paths[b], 15.0, 15, 0.1)
+        ora = CO.track(O.Params(horizon=15), rg, initial_state(paths[b], starts[b]), goals[b], T, polish_passes=3, **TIGHT)
+        n = int(res.n_steps[b])
+        assert n == ora["n_steps"]
+        assert np.abs(res.states[b, :n, :2] - ora["states"][:n, :2]).max() < 1e-3
