@@ -33,6 +33,7 @@ SEED = 3
 DU_DELTA = 0.02            # rad/step, configs[2] "tight steering-rate limits"
 EPS = 1e-6                 # parity setting of BASELINE.json (u0 within 1e-5 at eps_abs = eps_rel = 1e-6)
 POLISH_PASSES = 3
+POLISH_RETRY = 2
 
 # canonical flop model of BASELINE.md §2 / SURVEY.md §8d (n = 11N+5, m = 19N+7, nnz(A) = 43N+5)
 _NNZ_L = {15: 706, 20: 941, 50: 2349}
@@ -209,7 +210,7 @@ def main():
     N, B = HORIZON, args.batch
     warmup = max(3, args.warmup)
     params = product_params()
-    settings = SolverSettings(eps_abs=EPS, eps_rel=EPS, polish_passes=POLISH_PASSES)
+    settings = SolverSettings(eps_abs=EPS, eps_rel=EPS, polish_passes=POLISH_PASSES, polish_retry=POLISH_RETRY)
     start, count = shard_range(rank, world, B)
     x0, ref, up = make_batch(B * world, N, SEED, start=start, count=count)
     ctl = MPCController(params, settings, device=local_rank, max_batch=B)
@@ -301,7 +302,7 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{B} independent tracking QPs per GPU, horizon {N}, 4 states / 2 controls, steering-rate +-{DU_DELTA} rad/step "
                                f"(BASELINE.json configs[2]), seed {SEED}", "batch_per_gpu": B, "horizon": N, "eps_abs": EPS, "eps_rel": EPS,
-                   "polish_passes": POLISH_PASSES, "parallelism": f"{world} x independent shards, no data-path collective",
+                   "polish_passes": POLISH_PASSES, "polish_retry": POLISH_RETRY, "parallelism": f"{world} x independent shards, no data-path collective",
                    "l2": "working set per step (inputs 112 MB + outputs 161 MB + 803 MB warm-start state) exceeds the 126 MB L2; "
                          "a 256 MB write flushes L2 between timed steps"},
         "solve_stats": {"solved_frac": sum(m["solved"] for m in allm) / (B * world), "iters_mean": float(np.mean([m["iters_mean"] for m in allm])),

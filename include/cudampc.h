@@ -83,7 +83,8 @@ typedef struct cudampc_settings {
   int32_t polish_passes;         /* 0 = no polish, 1 = OSQP's polish, >1 = re-identify the active set up to n times */
   int32_t polish_refine_iter;
   int32_t warm_start;            /* 1: start from the iterate this handle stored for the same slot in the last call */
-  int32_t _pad;
+  int32_t polish_retry;          /* if OSQP's polish is rejected (active set not identified): resume ADMM at a 10x tighter
+                                    internal tolerance and polish again, up to this many times (0 = OSQP behaviour) */
 } cudampc_settings;
 
 /* Closed-loop constants of TrajectoryTracker.track (control_stage.py:84,141-150) */

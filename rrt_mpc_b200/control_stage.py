@@ -22,7 +22,7 @@ import numpy as np
 
 from . import _lib
 from .config import params_from_config
-from .mpc_controller import MPCController, MPCParameters, SolverSettings
+from .mpc_controller import MPCController, MPCParameters, SolverSettings, params_to_c
 from .ref_builder import build_reference
 from .vehicle_model import f_discrete
 
@@ -85,11 +85,12 @@ class TrajectoryTracker:
 
     def _controller(self, params: MPCParameters, key: str = "base") -> MPCController:
         cache = self.__dict__.setdefault("_controllers", {})
-        ctl = cache.get(key)
-        if ctl is None or ctl.params is not params and ctl.params != params:
-            ctl = MPCController(params, self.settings, device=self.device)
-            cache[key] = ctl
-        return ctl
+        fp = bytes(params_to_c(params))          # field-wise fingerprint (dataclass == is ambiguous on ndarray fields)
+        hit = cache.get(key)
+        if hit is None or hit[0] != fp:
+            hit = (fp, MPCController(params, self.settings, device=self.device))
+            cache[key] = hit
+        return hit[1]
 
     def track(self, planning, maps, *, map_resolution: float, visualize: bool = True, occupancy=None, axis=None) -> TrackingResult:
         plan = planning.plan

@@ -48,6 +48,7 @@ struct Settings {
   double adaptive_rho_tolerance, rho_eq_factor, rho_min, rho_max, delta;
   int max_iter, check_termination, adaptive_rho, adaptive_rho_interval;
   int polish_passes, polish_refine_iter, warm_start;
+  int polish_retry;   // resume ADMM at a tighter internal tolerance this many times if the polish is rejected
 };
 
 enum { STATUS_SOLVED = 1, STATUS_SOLVED_INACCURATE = 2, STATUS_MAX_ITER = -2, STATUS_UNSOLVED = -10 };

@@ -73,64 +73,74 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
   ex.factor(w); ++n_fac;
   ex.stages(NS, [&](int k) { admm_rhs_stage(w, p, s, rho, k); });
 
-  // ---- ADMM ------------------------------------------------------------------------------
+  // ---- ADMM + polish; a rejected polish (wrong active set) resumes ADMM at a 10x tighter internal tolerance ----
   int status = STATUS_UNSOLVED;
   int it = 0;
   Residuals res; res.pri = res.dua = 1e300; res.eps_p = res.eps_d = 0.0; res.sp = res.sd = 0.0; res.nz = res.nq = 0.0;
-  while (it < s.max_iter) {
-    ++it;
-    ex.tag(1); ex.solve(w); ++n_solve;
-    ex.tag(2); ex.stages(NS, [&](int k) { admm_update_stage(w, p, s, rho, k); admm_relax_x_stage(w, s, k); });
-    const bool check = (s.check_termination > 0) && (it % s.check_termination == 0);
-    const bool adapt = s.adaptive_rho && (s.adaptive_rho_interval > 0) && (it % s.adaptive_rho_interval == 0);
-    if (check || adapt) {
-      ex.tag(3); res = compute_residuals(ex, w, p, s, rho, 0);
-      if (check && res.pri <= res.eps_p && res.dua <= res.eps_d) { status = STATUS_SOLVED; break; }
-      if (adapt) {
-        double rho_new = rho * sqrt(res.sp / (res.sd + 1e-10));
-        rho_new = fmin(fmax(rho_new, s.rho_min), s.rho_max);
-        if (rho_new > rho * s.adaptive_rho_tolerance || rho_new < rho / s.adaptive_rho_tolerance) {
-          ex.stages(NS, [&](int k) { rescale_v_stage(w, p, rho, rho_new, k); });
-          rho = rho_new; ++n_rho;
-          mode = admm_mode(rho, s);
-          ex.tag(4); ex.stages(NS, [&](int k) { assemble_stage(w, p, mode, k); });
-          ex.tag(5); ex.factor(w); ++n_fac;
+  double pri = 1e300, dua = 1e300;
+  Settings se = s;                         // effective tolerances of the current attempt
+  for (int attempt = 0; attempt <= s.polish_retry; ++attempt) {
+    bool converged = false;
+    while (it < s.max_iter) {
+      ++it;
+      ex.tag(1); ex.solve(w); ++n_solve;
+      ex.tag(2); ex.stages(NS, [&](int k) { admm_update_stage(w, p, s, rho, k); admm_relax_x_stage(w, s, k); });
+      const bool check = (s.check_termination > 0) && (it % s.check_termination == 0);
+      const bool adapt = s.adaptive_rho && (s.adaptive_rho_interval > 0) && (it % s.adaptive_rho_interval == 0);
+      if (check || adapt) {
+        ex.tag(3); res = compute_residuals(ex, w, p, se, rho, 0);
+        if (check && res.pri <= res.eps_p && res.dua <= res.eps_d) { converged = true; break; }
+        if (adapt) {
+          double rho_new = rho * sqrt(res.sp / (res.sd + 1e-10));
+          rho_new = fmin(fmax(rho_new, s.rho_min), s.rho_max);
+          if (rho_new > rho * s.adaptive_rho_tolerance || rho_new < rho / s.adaptive_rho_tolerance) {
+            ex.stages(NS, [&](int k) { rescale_v_stage(w, p, rho, rho_new, k); });
+            rho = rho_new; ++n_rho;
+            mode = admm_mode(rho, s);
+            ex.tag(4); ex.stages(NS, [&](int k) { assemble_stage(w, p, mode, k); });
+            ex.tag(5); ex.factor(w); ++n_fac;
+          }
         }
       }
+      ex.tag(6); ex.stages(NS, [&](int k) { admm_rhs_stage(w, p, s, rho, k); });
     }
-    ex.tag(6); ex.stages(NS, [&](int k) { admm_rhs_stage(w, p, s, rho, k); });
-  }
-  ex.tag(7);
-  if (status != STATUS_SOLVED) {
-    res = compute_residuals(ex, w, p, s, rho, 0);
-    if (res.pri <= res.eps_p && res.dua <= res.eps_d) status = STATUS_SOLVED;
-    else {
-      double ep10 = 10.0 * s.eps_abs + 10.0 * (res.eps_p - s.eps_abs);
-      double ed10 = 10.0 * s.eps_abs + 10.0 * (res.eps_d - s.eps_abs);
-      status = (res.pri <= ep10 && res.dua <= ed10) ? STATUS_SOLVED_INACCURATE : STATUS_MAX_ITER;
+    ex.tag(7);
+    if (attempt == 0) {
+      if (converged) status = STATUS_SOLVED;
+      else {
+        res = compute_residuals(ex, w, p, s, rho, 0);
+        if (res.pri <= res.eps_p && res.dua <= res.eps_d) status = STATUS_SOLVED;
+        else {
+          double ep10 = 10.0 * s.eps_abs + 10.0 * (res.eps_p - s.eps_abs);
+          double ed10 = 10.0 * s.eps_abs + 10.0 * (res.eps_d - s.eps_abs);
+          status = (res.pri <= ep10 && res.dua <= ed10) ? STATUS_SOLVED_INACCURATE : STATUS_MAX_ITER;
+        }
+      }
+    } else if (!converged) {
+      res = compute_residuals(ex, w, p, se, rho, 0);
     }
-  }
-  double pri = res.pri, dua = res.dua;
+    pri = res.pri; dua = res.dua;
 
-  // ---- keep the ADMM iterate in HBM (warm start of the next call; polish back-up) ---------
-  if (io.warm) {
-    ex.stages(NS, [&](int k) { save_stage(w, k, io.warm); });
-    ex.single([&]() {
-      for (int r = 0; r < 4; ++r) io.warm[30 * NS + r] = w.hdr()[H_YI + r];
-      io.warm[30 * NS + 4] = rho;
-    });
-  }
+    // keep the ADMM iterate in HBM (warm start of the next call; polish back-up)
+    if (io.warm) {
+      ex.stages(NS, [&](int k) { save_stage(w, k, io.warm); });
+      ex.single([&]() {
+        for (int r = 0; r < 4; ++r) io.warm[30 * NS + r] = w.hdr()[H_YI + r];
+        io.warm[30 * NS + 4] = rho;
+      });
+    }
+    if (!(status == STATUS_SOLVED && s.polish_passes > 0 && io.warm && io.scratch)) break;
 
-  // ---- polish (OSQP polish = pass 1; further passes re-identify the active set from Ax + y) ----
-  if (status == STATUS_SOLVED && s.polish_passes > 0 && io.warm && io.scratch) {
+    // polish (OSQP polish = pass 1; further passes re-identify the active set from Ax + y)
     const Mode pm = polish_mode(s);
+    bool settled = false;                  // the active set stopped changing (or only one pass was asked for)
     for (int pass = 0; pass < s.polish_passes; ++pass) {
       if (pass > 0) {
         ex.stages(NS, [&](int k) { save_stage(w, k, io.scratch); });
         ex.single([&]() { for (int r = 0; r < 4; ++r) io.scratch[30 * NS + r] = w.hdr()[H_YI + r]; });
       }
       int changed = ex.any(NS, [&](int k) { return polish_activity_stage(w, p, rho, pass == 0, k); });
-      if (pass > 0 && !changed) break;
+      if (pass > 0 && !changed) { settled = true; break; }
       ex.stages(NS, [&](int k) { polish_zero_stage(w, k); });
       ex.stages(NS, [&](int k) { assemble_stage(w, p, pm, k); });
       ex.factor(w); ++n_fac;
@@ -155,6 +165,19 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
         break;
       }
     }
+    // a clean polish solves the KKT system of a settled active set to round-off
+    const bool clean = n_pol > 0 && (settled || s.polish_passes == 1) &&
+                       pri <= 1e-9 * dmax(1.0, res.nz) && dua <= 1e-9 * dmax(1.0, res.nq);
+    if (clean || attempt == s.polish_retry || it >= s.max_iter) break;
+    // active set not identified (polish rejected, still changing, or left a residual): back to the ADMM iterate,
+    // tighten the internal tolerance and iterate on
+    n_pol = 0;
+    ex.stages(NS, [&](int k) { load_stage(w, k, io.warm); });
+    ex.single([&]() { for (int r = 0; r < 4; ++r) w.hdr()[H_YI + r] = io.warm[30 * NS + r]; });
+    se.eps_abs *= 0.1; se.eps_rel *= 0.1;
+    ex.stages(NS, [&](int k) { assemble_stage(w, p, mode, k); });      // the polish factor replaced the ADMM factor
+    ex.factor(w); ++n_fac;
+    ex.stages(NS, [&](int k) { admm_rhs_stage(w, p, s, rho, k); });
   }
 
   // ---- outputs (mpc_controller.py:141: U[:,0], X (4,N+1), U (2,N)) --------------------------

@@ -63,6 +63,7 @@ class SolverSettings:
     delta: float = 1e-6
     polish_refine_iter: int = 3
     warm_start: bool = False      # upstream's warm_start=True is a no-op (a new Problem per call)
+    polish_retry: int = 0         # rejected polish -> resume ADMM at 10x tighter internal eps, polish again (0 = OSQP)
 
     def to_c(self) -> _lib.Settings:
         lib = _lib.load()
@@ -74,6 +75,7 @@ class SolverSettings:
         s.check_termination, s.adaptive_rho_interval = int(self.check_termination), int(self.adaptive_rho_interval)
         s.adaptive_rho_tolerance, s.delta = self.adaptive_rho_tolerance, self.delta
         s.polish_refine_iter, s.warm_start = int(self.polish_refine_iter), int(self.warm_start)
+        s.polish_retry = int(self.polish_retry)
         return s
 
 

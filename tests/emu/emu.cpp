@@ -38,7 +38,7 @@ int emu_warm_size(int N) { return warm_size(N); }
 // params/settings passed as flat double arrays to keep the ctypes side trivial
 //  par: L, dt, q[4], r[2], qn[4], u_lo[2], u_hi[2], v_lo, v_hi, du_lo[2], du_hi[2], w_v, w_u, w_du   (25)
 //  set: eps_abs, eps_rel, rho0, alpha, sigma, adaptive_rho_tolerance, rho_eq_factor, rho_min, rho_max, delta,
-//       max_iter, check_termination, adaptive_rho, adaptive_rho_interval, polish_passes, polish_refine_iter, warm_start (17)
+//       max_iter, check_termination, adaptive_rho, adaptive_rho_interval, polish_passes, polish_refine_iter, warm_start, polish_retry (18)
 static void unpack(const double* par, const double* set, int N, Params& p, Settings& s) {
   int i = 0;
   p.L = par[i++]; p.dt = par[i++];
@@ -58,7 +58,7 @@ static void unpack(const double* par, const double* set, int N, Params& p, Setti
   s.delta = set[i++];
   s.max_iter = (int)set[i++]; s.check_termination = (int)set[i++]; s.adaptive_rho = (int)set[i++];
   s.adaptive_rho_interval = (int)set[i++]; s.polish_passes = (int)set[i++]; s.polish_refine_iter = (int)set[i++];
-  s.warm_start = (int)set[i++];
+  s.warm_start = (int)set[i++]; s.polish_retry = (int)set[i++];
 }
 
 int emu_solve_batch(const double* par, const double* set, int N, int B, int reverse,

@@ -12,7 +12,7 @@ from conftest import ROOT, product_params
 def header_symbols():
     src = open(os.path.join(ROOT, "include", "cudampc.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(cudampc_[a-z_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(cudampc_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_library_exports_every_declared_symbol():

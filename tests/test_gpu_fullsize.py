@@ -29,7 +29,7 @@ def test_full_size_batches(N, B, du, seed):
     from rrt_mpc_b200.synthetic import make_batch
     from oracle import mpc_numpy as O
     x0, ref, up = make_batch(B, N, seed)
-    ctl = MPCController(product_params(N, du), SolverSettings(polish_passes=3, **TIGHT), max_batch=B)
+    ctl = MPCController(product_params(N, du), SolverSettings(polish_passes=3, polish_retry=2, **TIGHT), max_batch=B)
     d = lambda a: torch.as_tensor(a).cuda()
     dx0, dref, dup = d(x0), d(ref), d(up)
     rd = ctl.solve_batch(dx0, dref, u_prev=dup)
@@ -40,8 +40,8 @@ def test_full_size_batches(N, B, du, seed):
     assert np.array_equal(r.u0, r.Up[:, :, 0])                            # u0 is U[:, 0]
     # polished problems satisfy the KKT system to round-off; the rest to the ADMM tolerance
     pol = r.info[:, 2] > 0
-    assert pol.mean() > 0.9
-    assert r.pri_res[pol].max() < 1e-8 and r.dua_res[pol].max() < 1e-7
+    assert pol.mean() > 0.999                                             # polish (with retry) succeeds essentially everywhere
+    assert r.pri_res[pol].max() < 1e-6 and r.dua_res[pol].max() < 1e-6     # |x| ~ 3e2, |q| ~ 2e3: relative 1e-9
     A, Bm, c = (t.cpu().numpy() for t in ctl.linearize_batch(dref))
     dyn, init = kkt_check(oracle_params(N, du), x0, ref, up, r, A, Bm, c)
     assert init < 1e-3 and dyn < 1e-3                                     # unpolished tail: eps_rel * |x| ~ 3e-4

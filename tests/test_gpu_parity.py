@@ -10,9 +10,9 @@ pytestmark = pytest.mark.gpu
 TIGHT = dict(eps_abs=1e-6, eps_rel=1e-6)
 
 
-def controller(N, du=0.15, passes=3, max_batch=64, **kw):
+def controller(N, du=0.15, passes=3, max_batch=64, retry=2, **kw):
     from rrt_mpc_b200 import MPCController, SolverSettings
-    return MPCController(product_params(N, du), SolverSettings(polish_passes=passes, **{**TIGHT, **kw}), max_batch=max_batch)
+    return MPCController(product_params(N, du), SolverSettings(polish_passes=passes, polish_retry=retry, **{**TIGHT, **kw}), max_batch=max_batch)
 
 
 def test_extension_is_loaded_and_counts_launches():
@@ -54,7 +54,7 @@ def test_status_and_iterations_identical_to_oracle(name, N, du):
     from oracle import c_oracle as CO
     g = load_golden("optima.npz")
     nb = 12
-    ctl = controller(N, du, passes=1)
+    ctl = controller(N, du, passes=1, retry=0)
     r = ctl.solve_batch(g[f"{name}_x0"][:nb], g[f"{name}_ref"][:nb], u_prev=g[f"{name}_up"][:nb])
     # mirror mode: the same ADMM on the same QP, solved through a generic sparse KKT LDL' on the CPU
     c = CO.solve_batch(oracle_params(N, du), g[f"{name}_x0"][:nb], g[f"{name}_ref"][:nb], g[f"{name}_up"][:nb], scaling=0, z0_projected=1, **TIGHT)
@@ -73,7 +73,7 @@ def test_matches_host_emulation_of_the_same_source():
     g = load_golden("optima.npz")
     ctl = controller(20)
     r = ctl.solve_batch(g["n20_x0"][:8], g["n20_ref"][:8], u_prev=g["n20_up"][:8])
-    e = E.solve(oracle_params(20), g["n20_x0"][:8], g["n20_ref"][:8], g["n20_up"][:8], polish_passes=3, **TIGHT)
+    e = E.solve(oracle_params(20), g["n20_x0"][:8], g["n20_ref"][:8], g["n20_up"][:8], polish_passes=3, polish_retry=2, **TIGHT)
     assert np.array_equal(r.iters, e["iters"]) and np.array_equal(r.status, e["status"])
     assert np.abs(r.u0 - e["u0"]).max() < 1e-10 and np.abs(r.Xp - e["Xp"]).max() < 1e-9
 
