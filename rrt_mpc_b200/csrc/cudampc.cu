@@ -14,123 +14,9 @@
 #include <new>
 
 #include "../../include/cudampc.h"
-#include "mpc_solve.h"
+#include "mpc_exec.cuh"
 
 using namespace mpc;
-
-// ------------------------------------------------------------------------------------------------
-// Warp execution policy
-// ------------------------------------------------------------------------------------------------
-struct WarpExec {
-  int lane;
-  __device__ __forceinline__ void tag(int) {}
-  template <class F> __device__ __forceinline__ void stages(int n, F f) {
-    for (int k = lane; k < n; k += 32) f(k);
-    __syncwarp();
-  }
-  template <class F> __device__ __forceinline__ void single(F f) {
-    if (lane == 0) f();
-    __syncwarp();
-  }
-  template <class F> __device__ __forceinline__ void reduce_max(int n, double* r, int nr, F f) {
-    for (int i = 0; i < nr; ++i) r[i] = 0.0;
-    for (int k = lane; k < n; k += 32) f(k, r);
-    for (int i = 0; i < nr; ++i) {
-      double v = r[i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-      r[i] = v;
-    }
-    __syncwarp();
-  }
-  template <class F> __device__ __forceinline__ int any(int n, F f) {
-    int a = 0;
-    for (int k = lane; k < n; k += 32) a |= f(k);
-    a = __any_sync(0xffffffffu, a);
-    __syncwarp();
-    return a;
-  }
-  __device__ __forceinline__ void factor(const View& w) {
-    if (lane == 0) factor_band(w);
-    __syncwarp();
-  }
-  __device__ __forceinline__ void solve(const View& w) {
-    if (lane == 0) chain_solve(w);
-    __syncwarp();
-  }
-};
-
-// ------------------------------------------------------------------------------------------------
-// CTA execution policy ("transposed chain"): the CTA holds P problems, warp p runs the stage-parallel
-// phases of problem p, and the sequential triangular sweeps of ALL P problems run in lock step in warp 0
-// with lanes = problems (one DFMA warp-instruction then serves P problems instead of one lane).  A chain
-// operation is a rendezvous round: [bar] warp 0 sweeps every problem that posted a request [bar].
-// Factorisations run in the owner warp, chunked over rounds, overlapped with the other problems' sweeps.
-// ------------------------------------------------------------------------------------------------
-struct CtaShared {
-  int req[32];
-  int active;      // warps that still have work; read only between the two barriers of a round
-};
-
-__device__ __forceinline__ void cta_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
-
-struct CtaExec {
-  int lane, warp, P, N, F;
-  double* smem0;
-  CtaShared* sh;
-  int chunk;       // factor stages per round
-  __device__ __forceinline__ void tag(int) {}
-  template <class Fn> __device__ __forceinline__ void stages(int n, Fn f) {
-    for (int k = lane; k < n; k += 32) f(k);
-    __syncwarp();
-  }
-  template <class Fn> __device__ __forceinline__ void single(Fn f) {
-    if (lane == 0) f();
-    __syncwarp();
-  }
-  template <class Fn> __device__ __forceinline__ void reduce_max(int n, double* r, int nr, Fn f) {
-    for (int i = 0; i < nr; ++i) r[i] = 0.0;
-    for (int k = lane; k < n; k += 32) f(k, r);
-    for (int i = 0; i < nr; ++i) {
-      double v = r[i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-      r[i] = v;
-    }
-    __syncwarp();
-  }
-  template <class Fn> __device__ __forceinline__ int any(int n, Fn f) {
-    int a = 0;
-    for (int k = lane; k < n; k += 32) a |= f(k);
-    a = __any_sync(0xffffffffu, a);
-    __syncwarp();
-    return a;
-  }
-  // one rendezvous round; kind 0 none, 1 sweep request, 2 factor chunk [i0,i1) in the owner warp
-  __device__ __forceinline__ int round(int kind, const View& w, int i0, int i1) {
-    if (lane == 0) sh->req[warp] = (kind == 1);
-    cta_bar(32 * P);
-    const int snap = sh->active;
-    if (warp == 0) {
-      if (lane < P && sh->req[lane]) { View v{smem0 + (size_t)lane * F, N}; chain_solve(v); }
-      if (kind == 2 && lane == 0) factor_stages(w, i0, i1);
-      __syncwarp();
-    } else if (kind == 2 && lane == 0) {
-      factor_stages(w, i0, i1);
-    }
-    cta_bar(32 * P);
-    return snap;
-  }
-  __device__ __forceinline__ void solve(const View& w) { round(1, w, 0, 0); }
-  __device__ __forceinline__ void factor(const View& w) {
-    const int n = N + 1;
-    for (int i0 = 0; i0 < n; i0 += chunk) round(2, w, i0, min(i0 + chunk, n));
-  }
-  __device__ __forceinline__ void drain() {
-    if (lane == 0) atomicSub(&sh->active, 1);
-    while (round(0, View{smem0, N}, 0, 0) > 0) {}
-  }
-};
 
 struct BatchArgs {
   const double* x0; const double* ref; const double* u_prev;
@@ -174,7 +60,9 @@ __global__ void __launch_bounds__(32) mpc_solve_kernel(Params p, Settings s, Bat
   }
 }
 
-__global__ void __launch_bounds__(512) mpc_solve_cta_kernel(Params p, Settings s, BatchArgs a, int P, int F, int chunk) {
+// MAXT = 256: up to 8 problems per CTA, 255 registers (software-pipelined sweeps); MAXT = 512: up to 16, 128 registers
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) mpc_solve_cta_kernel(Params p, Settings s, BatchArgs a, int P, int F, int chunk) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int N = p.N;
@@ -183,7 +71,7 @@ __global__ void __launch_bounds__(512) mpc_solve_cta_kernel(Params p, Settings s
   if (threadIdx.x < 32) sh->req[threadIdx.x] = 0;
   __syncthreads();
   View w{smem + (size_t)warp * F, N};
-  CtaExec ex{lane, warp, P, N, F, smem, sh, chunk};
+  CtaExec<false> ex{lane, warp, P, N, F, smem, sh, chunk};   // the hand-pipelined sweeps (PIPE) gain <10% and cost 190 registers
   const int ws = warm_size(N);
   for (int b = next_problem(a.counter, lane); b < a.batch; b = next_problem(a.counter, lane)) {
     ProblemIO io;
@@ -480,11 +368,12 @@ int cudampc_create(const cudampc_params* params, int max_batch, int device, cuda
     if (P > 16) P = 16;
     h->cta_P = P;
     h->cta_smem = P * F * (int)sizeof(double) + (int)sizeof(CtaShared) + 16;
-    h->cta_chunk = (p.N + 1 + 2) / 3;        // a factorisation spreads over 3 rounds
+    h->cta_chunk = (half_bot(p.N) + 1) / 2;  // a (twisted) factorisation spreads over 2 rounds
     const char* env = getenv("CUDAMPC_KERNEL");
     h->use_cta = (P >= 2) && !(env && strcmp(env, "warp") == 0);
     if (h->use_cta) {
-      e = cudaFuncSetAttribute(mpc_solve_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta_smem);
+      e = (P <= 8) ? cudaFuncSetAttribute(mpc_solve_cta_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta_smem)
+                   : cudaFuncSetAttribute(mpc_solve_cta_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta_smem);
       if (e != cudaSuccess) { delete h; return fail(nullptr, CUDAMPC_ERR_CUDA, "CUDA failure: %s", cudaGetErrorString(e)); }
       h->per_sm = P;
     }
@@ -596,7 +485,8 @@ int cudampc_solve_batch(cudampc_handle* h, int batch, const double* x0_dev, cons
   if (h->use_cta) {
     int grid = (batch + h->cta_P - 1) / h->cta_P;
     if (grid > h->sms) grid = h->sms;
-    mpc_solve_cta_kernel<<<grid, 32 * h->cta_P, h->cta_smem, st>>>(h->p, s, a, h->cta_P, footprint(h->N), h->cta_chunk);
+    if (h->cta_P <= 8) mpc_solve_cta_kernel<256><<<grid, 32 * h->cta_P, h->cta_smem, st>>>(h->p, s, a, h->cta_P, footprint(h->N), h->cta_chunk);
+    else mpc_solve_cta_kernel<512><<<grid, 32 * h->cta_P, h->cta_smem, st>>>(h->p, s, a, h->cta_P, footprint(h->N), h->cta_chunk);
   } else {
     int grid = h->sms * h->per_sm;
     if (grid > batch) grid = batch;

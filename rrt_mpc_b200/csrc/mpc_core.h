@@ -85,17 +85,32 @@ enum { BLK = 44 };
 #define MPC_ID(j) (15 + (j))
 #define MPC_IC(j, jp) (22 + 6 * (j) - (j) * ((j) - 1) / 2 + ((jp) - (j)))
 
+// Twisted ("burn at both ends") organisation of the banded system: stages 0..m are eliminated top-down, stages
+// N..m+1 bottom-up, both ending at the middle stage m = N/2.  The bottom half is STORED in reversed order
+// (stage N-i at local index i, in-stage index 5-j): the reversed system has exactly the same band structure, so
+// one instruction stream sweeps a top half in one lane and a bottom half in another, halving the chain length.
+MPC_HD int mid_stage(int N) { return N / 2; }
+MPC_HD int half_top(int N) { return mid_stage(N) + 1; }          // local stages of the top half (last = middle = border)
+MPC_HD int half_bot(int N) { return N - mid_stage(N) + 1; }      // local stages of the bottom half (last = middle = border)
+MPC_HD int bx_doubles(int N) { return 7 * (half_top(N) + 2) + 7 * (half_bot(N) + 2); }
 MPC_HD int band_offset(int N) {           // even => 16-byte aligned blocks
-  int o = hdr_size(N) + (N + 1) * SR + 7 * (N + 3);
+  int o = hdr_size(N) + (N + 1) * SR + bx_doubles(N);
   return (o + 1) & ~1;
 }
 MPC_HD int footprint(int N) {
-  int f = band_offset(N) + BLK * (N + 2);
+  int f = band_offset(N) + BLK * (half_top(N) + 1) + BLK * (half_bot(N) + 1) + 22;
   while ((f & 3) != 2) ++f;               // F = 2 (mod 4): conflict-free 128-bit loads when lanes stride over problems
   return f;
 }
 // warm-start state kept in HBM between calls: per stage xu(6) s(5) v(15) ye(4), + yi(4) + rho
 MPC_HD int warm_size(int N) { return 30 * (N + 1) + 5; }
+
+// one half of the twisted system as the chain code sees it (local stage index i = 0 .. H-1, border = H-1)
+struct HalfView {
+  double* bx0; double* blk0; int H;
+  MPC_HD double* bx(int i) const { return bx0 + 7 * i; }         // i = -1 .. H
+  MPC_HD double* blk(int i) const { return blk0 + BLK * i; }     // i = 0 .. H
+};
 
 struct View {
   double* base;
@@ -103,8 +118,23 @@ struct View {
   MPC_HD double* hdr() const { return base; }
   MPC_HD int* act() const { return reinterpret_cast<int*>(base + H_ACT); }  // [N+1] stage masks + [N+1]=init rows
   MPC_HD double* rec(int k) const { return base + hdr_size(N) + k * SR; }
-  MPC_HD double* bx(int k) const { return base + hdr_size(N) + (N + 1) * SR + 7 * (k + 1); }       // k = -1 .. N+1
-  MPC_HD double* blk(int k) const { return base + band_offset(N) + BLK * k; }                      // k = 0 .. N+1
+  MPC_HD double* bx_base() const { return base + hdr_size(N) + (N + 1) * SR; }
+  MPC_HD double* scratch() const { return bx_base(); }                       // >= N+1 doubles, free before the first solve
+  MPC_HD HalfView top() const { return HalfView{bx_base() + 7, base + band_offset(N), half_top(N)}; }
+  MPC_HD HalfView bottom() const {
+    return HalfView{bx_base() + 7 * (half_top(N) + 2) + 7, base + band_offset(N) + BLK * (half_top(N) + 1), half_bot(N)};
+  }
+  MPC_HD double* mid() const { return base + band_offset(N) + BLK * (half_top(N) + 1) + BLK * (half_bot(N) + 1); }
+  // element (k, j) of the right-hand side / solution vector in the twisted storage
+  MPC_HD double bx_get(int k, int j) const {
+    const int m = mid_stage(N);
+    return k <= m ? top().bx(k)[j] : bottom().bx(N - k)[5 - j];
+  }
+  MPC_HD void bx_set(int k, int j, double v) const {
+    const int m = mid_stage(N);
+    if (k <= m) top().bx(k)[j] = v; else bottom().bx(N - k)[5 - j] = v;
+    if (k == m) bottom().bx(N - m)[5 - j] = 0.0;      // the bottom half's copy of the middle stage carries no rhs
+  }
 };
 
 struct alignas(16) D2 { double x, y; };   // 128-bit shared-memory access (blocks are 16-byte aligned)
@@ -251,7 +281,7 @@ MPC_HD double group_g(int k, int g, const XV& xv) {
 }
 
 struct StateXV { View w; MPC_HD double operator()(int k, int j) const { return w.rec(k)[R_XU + j]; } };
-struct BxXV { View w; MPC_HD double operator()(int k, int j) const { return w.bx(k)[j]; } };
+struct BxXV { View w; MPC_HD double operator()(int k, int j) const { return w.bx_get(k, j); } };
 
 // ----------------------------------------------------------------------------------------------
 // Problem setup
@@ -324,28 +354,37 @@ MPC_HD int act_group_bits(const View& w, int k, int g) { return (w.act()[k] >> (
 MPC_HD int act_dyn_bit(const View& w, int k, int r) { return (w.act()[k] >> (15 + r)) & 1; }
 MPC_HD int act_init_bit(const View& w, int r) { return (w.act()[w.N + 1] >> r) & 1; }
 
-MPC_HD void assemble_stage(const View& w, const Params& p, const Mode& m, int k) {
+// E = M[stage k rows][stage k-1 cols] (k >= 1): dynamics rows of stage k-1 and the rate groups of stage k
+MPC_HD void stage_cross(const View& w, const Params& p, const Mode& m, int k, double E[6][6]) {
+  for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) E[a][b] = 0.0;
+  const double* lin = w.rec(k - 1) + R_LIN;
+  double om[4];
+  for (int r = 0; r < 4; ++r) om[r] = eq_weight(m, m.polish ? act_dyn_bit(w, k - 1, r) : 1);
+  // row r of stage k-1: +1 at x_k[r], -(A,B) part on stage k-1  =>  E[r][:] = om[r] * a_r^{(k-1)}
+  E[0][0] = -om[0]; E[0][2] = -om[0] * lin[0]; E[0][3] = -om[0] * lin[1];
+  E[1][1] = -om[1]; E[1][2] = -om[1] * lin[2]; E[1][3] = -om[1] * lin[3];
+  E[2][2] = -om[2]; E[2][5] = -om[2] * lin[4];
+  E[3][3] = -om[3]; E[3][4] = -om[3] * p.dt;
+  if (k < w.N) {
+    for (int i = 0; i < 2; ++i) {
+      GroupCoef cd = group_coef(m, group_ps(p, 3 + i), m.polish ? act_group_bits(w, k, 3 + i) : 0);
+      E[4 + i][4 + i] -= cd.kappa;                            // (u_k - u_{k-1}) coupling
+    }
+  }
+}
+// D = diagonal block of stage k (lower part filled; dummy unknowns of the terminal stage are identity rows)
+MPC_HD void stage_diag(const View& w, const Params& p, const Mode& m, int k, double D[6][6]) {
   const int N = w.N;
-  const int nj = k < N ? 6 : 4;
-  double D[6][6], E[6][6];   // D: diagonal block (lower part used); E: coupling to stage k-1 (rows k, cols k-1)
-  for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) { D[a][b] = 0.0; E[a][b] = 0.0; }
+  for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) D[a][b] = 0.0;
   const double* qd = k < N ? p.q : p.qn;
   for (int j = 0; j < 4; ++j) D[j][j] = 2.0 * qd[j] + m.reg;
   if (k < N) { D[4][4] = 2.0 * p.r[0] + m.reg; D[5][5] = 2.0 * p.r[1] + m.reg; }
+  else { D[4][4] = 1.0; D[5][5] = 1.0; }
   // rows arriving at x_k: init rows (k == 0) or dynamics rows of stage k-1
   if (k == 0) {
     for (int r = 0; r < 4; ++r) D[r][r] += eq_weight(m, m.polish ? act_init_bit(w, r) : 1);
   } else {
-    const double* lin = w.rec(k - 1) + R_LIN;
-    double om[4];
-    for (int r = 0; r < 4; ++r) om[r] = eq_weight(m, m.polish ? act_dyn_bit(w, k - 1, r) : 1);
-    // row r of stage k-1: +1 at x_k[r], -(A,B) part on stage k-1
-    for (int r = 0; r < 4; ++r) D[r][r] += om[r];
-    // E[r][:] = om[r] * a_r^{(k-1)}
-    E[0][0] = -om[0]; E[0][2] = -om[0] * lin[0]; E[0][3] = -om[0] * lin[1];
-    E[1][1] = -om[1]; E[1][2] = -om[1] * lin[2]; E[1][3] = -om[1] * lin[3];
-    E[2][2] = -om[2]; E[2][5] = -om[2] * lin[4];
-    E[3][3] = -om[3]; E[3][4] = -om[3] * p.dt;
+    for (int r = 0; r < 4; ++r) D[r][r] += eq_weight(m, m.polish ? act_dyn_bit(w, k - 1, r) : 1);
   }
   if (k < N) {
     const double* lin = w.rec(k) + R_LIN;
@@ -370,38 +409,58 @@ MPC_HD void assemble_stage(const View& w, const Params& p, const Mode& m, int k)
       GroupCoef cu = group_coef(m, group_ps(p, 1 + i), m.polish ? act_group_bits(w, k, 1 + i) : 0);
       GroupCoef cd = group_coef(m, group_ps(p, 3 + i), m.polish ? act_group_bits(w, k, 3 + i) : 0);
       D[4 + i][4 + i] += cu.kappa + cd.kappa;
-      if (k > 0) E[4 + i][4 + i] -= cd.kappa;                 // (u_k - u_{k-1}) coupling
       if (k + 1 < N) {
         GroupCoef cn = group_coef(m, group_ps(p, 3 + i), m.polish ? act_group_bits(w, k + 1, 3 + i) : 0);
         D[4 + i][4 + i] += cn.kappa;
       }
     }
   }
-  double* b = w.blk(k);
-  for (int j = 0; j < 6; ++j) {
-    if (j < nj) {
+}
+
+// Write stage k's blocks in the twisted storage.  Top half (k <= m): in-stage = D_k, cross = E_k (to stage k-1).
+// Bottom half (k >= m), local index i = N-k, everything index-reversed: in-stage = rev(D_k) (zero for the border
+// k = m, which only collects the bottom half's Schur complement), cross = rev(E_{k+1}') (to stage k+1).
+MPC_HD void assemble_stage(const View& w, const Params& p, const Mode& m, int k) {
+  const int N = w.N;
+  const int ms = mid_stage(N);
+  double D[6][6], E[6][6];
+  stage_diag(w, p, m, k, D);
+  if (k <= ms) {
+    double* b = w.top().blk(k);
+    if (k > 0) stage_cross(w, p, m, k, E);
+    for (int j = 0; j < 6; ++j) {
       for (int jp = 0; jp < j; ++jp) b[MPC_IA(j, jp)] = D[j][jp];
       b[MPC_ID(j)] = D[j][j];
       for (int jp = j; jp < 6; ++jp) b[MPC_IC(j, jp)] = (k > 0) ? E[j][jp] : 0.0;
-    } else {            // dummy unknowns of the terminal stage
-      for (int jp = 0; jp < j; ++jp) b[MPC_IA(j, jp)] = 0.0;
-      b[MPC_ID(j)] = 1.0;
-      for (int jp = j; jp < 6; ++jp) b[MPC_IC(j, jp)] = 0.0;
     }
+    b[21] = 0.0; b[43] = 0.0;
   }
-  b[21] = 0.0; b[43] = 0.0;
+  if (k >= ms) {
+    double* b = w.bottom().blk(N - k);
+    if (k < N) stage_cross(w, p, m, k + 1, E);     // E = M[stage k+1 rows][stage k cols]
+    const bool border = (k == ms);
+    for (int j = 0; j < 6; ++j) {                  // local (reversed) indices j, jp  <->  global 5-j, 5-jp
+      for (int jp = 0; jp < j; ++jp) b[MPC_IA(j, jp)] = border ? 0.0 : D[5 - jp][5 - j];
+      b[MPC_ID(j)] = border ? 0.0 : D[5 - j][5 - j];
+      // local cross entry (row j of this stage, col jp >= j of the previous local stage = global stage k+1):
+      //   M[(k, 5-j)][(k+1, 5-jp)] = E[5-jp][5-j]
+      for (int jp = j; jp < 6; ++jp) b[MPC_IC(j, jp)] = (k < N) ? E[5 - jp][5 - j] : 0.0;
+    }
+    b[21] = 0.0; b[43] = 0.0;
+  }
 }
 
 // ----------------------------------------------------------------------------------------------
-// Banded LDL' (unit lower L, half-bandwidth 6) as a right-looking block algorithm over stages, everything
-// of one stage staged in registers: factor the 6x6 in-stage block, form the cross block of the next stage,
-// apply its Schur complement to the next stage's in-stage block.  Sequential over stages [k0, k1).
+// Banded LDL' (unit lower L, half-bandwidth 6) as a right-looking block algorithm over the local stages of one
+// half, everything of a stage staged in registers: factor the 6x6 in-stage block, form the cross block of the next
+// stage, apply its Schur complement to the next stage's in-stage block.  Sequential over local stages [i0, i1),
+// i1 <= H-1 (the border stage is never eliminated inside a half).
 //   after: IA = L in-stage, ID = 1/D, IC = L cross
 // ----------------------------------------------------------------------------------------------
-MPC_HD void factor_stages(const View& w, int k0, int k1) {
-  const int N = w.N;
-  for (int k = k0; k < k1; ++k) {
-    double* __restrict__ Bk = w.blk(k);
+MPC_HD void factor_half(const HalfView& h, int i0, int i1) {
+  if (i1 > h.H - 1) i1 = h.H - 1;
+  for (int k = i0; k < i1; ++k) {
+    double* __restrict__ Bk = h.blk(k);
     double S[6][6], Lm[6][6], dinv[6];
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
@@ -426,8 +485,8 @@ MPC_HD void factor_stages(const View& w, int k0, int k1) {
       for (int jp = 0; jp < j; ++jp) Bk[MPC_IA(j, jp)] = Lm[j][jp];
       Bk[MPC_ID(j)] = dinv[j];
     }
-    if (k < N) {
-      double* __restrict__ Bn = w.blk(k + 1);
+    {
+      double* __restrict__ Bn = h.blk(k + 1);
       double Wc[6][6], Cl[6][6];
 #pragma unroll
       for (int j = 0; j < 6; ++j)
@@ -454,31 +513,78 @@ MPC_HD void factor_stages(const View& w, int k0, int k1) {
     }
   }
 }
-MPC_HD void factor_band(const View& w) { factor_stages(w, 0, w.N + 1); }
+// Middle stage: S_m = (top border in-stage block) + reversed(bottom border in-stage block); LDL' into mid();
+// then clear the borders' in-stage parts so that the backward sweeps start from them with the plain stage step.
+MPC_HD void factor_middle(const View& w) {
+  HalfView T = w.top(), B = w.bottom();
+  double* bt = T.blk(T.H - 1); double* bb = B.blk(B.H - 1); double* md = w.mid();
+  double S[6][6];
+  for (int r = 0; r < 6; ++r)
+    for (int c = 0; c <= r; ++c) {
+      double top = r == c ? bt[MPC_ID(r)] : bt[MPC_IA(r, c)];
+      const int rr = 5 - c, cc = 5 - r;                                    // reversed position (rr >= cc)
+      double bot = rr == cc ? bb[MPC_ID(rr)] : bb[MPC_IA(rr, cc)];
+      S[r][c] = top + bot;
+    }
+  double dinv[6];
+  for (int jp = 0; jp < 6; ++jp) {
+    dinv[jp] = 1.0 / S[jp][jp];
+    for (int j = jp + 1; j < 6; ++j) {
+      const double l = S[j][jp] * dinv[jp];
+      for (int j2 = jp + 1; j2 <= j; ++j2) S[j][j2] -= l * S[j2][jp];
+      md[MPC_IA(j, jp)] = l;
+    }
+    md[MPC_ID(jp)] = dinv[jp];
+  }
+  for (int i = 0; i < 21; ++i) { bt[i] = 0.0; bb[i] = 0.0; }
+}
+// x = S_m^{-1} a  (6x6 LDL' in mid())
+MPC_HD void middle_solve(const View& w, const double* a, double* x) {
+  const double* md = w.mid();
+  double y[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double v = a[j];
+#pragma unroll
+    for (int jp = 0; jp < j; ++jp) v = fma(-md[MPC_IA(j, jp)], y[jp], v);
+    y[j] = v;
+  }
+#pragma unroll
+  for (int j = 5; j >= 0; --j) {
+    double v = y[j] * md[MPC_ID(j)];
+#pragma unroll
+    for (int jp = j + 1; jp < 6; ++jp) v = fma(-md[MPC_IA(jp, j)], x[jp], v);
+    x[j] = v;
+  }
+}
+// whole twisted factorisation, sequential (host emulation / single-lane use)
+MPC_HD void factor_band(const View& w) {
+  HalfView T = w.top(), B = w.bottom();
+  factor_half(T, 0, T.H - 1);
+  factor_half(B, 0, B.H - 1);
+  factor_middle(w);
+}
 
-// Solve L D L' x = b in place on bx (stride 7 per stage), sequential, in column-oriented (axpy) form:
-// as soon as a pivot value is known it is pushed into the accumulators of the six rows that depend on
-// it, so only ONE fma separates consecutive pivots and the other five issue in its shadow (the SM issues
-// in order; a dot-product formulation would serialise six dependent fmas per row).  The factor block of a
-// stage is staged in registers before any arithmetic so that the shared-memory latency is paid once per
-// stage, not once per fma.
+// Triangular sweeps of one half in column-oriented (axpy) form: as soon as a pivot value is known it is pushed
+// into the accumulators of the six rows that depend on it, so only ONE fma separates consecutive pivots and the
+// other five issue in its shadow (the SM issues in order; a dot-product formulation would serialise six dependent
+// fmas per row).  The factor block of a stage is staged in registers with 128-bit loads before any arithmetic.
 struct ChainRegs { double la[22], lc[22], nb[6]; };
 
-// stage the factor block(s) and the next right-hand side of one forward / backward stage in registers
-MPC_HD void chain_load_fwd(const View& w, int k, ChainRegs& r) {
-  const D2* __restrict__ pa = reinterpret_cast<const D2*>(w.blk(k));
-  const D2* __restrict__ pc = reinterpret_cast<const D2*>(w.blk(k + 1) + 22);
+MPC_HD void chain_load_fwd(const HalfView& h, int k, ChainRegs& r) {
+  const D2* __restrict__ pa = reinterpret_cast<const D2*>(h.blk(k));
+  const D2* __restrict__ pc = reinterpret_cast<const D2*>(h.blk(k + 1) + 22);
 #pragma unroll
   for (int i = 0; i < 11; ++i) { D2 u = pa[i], v = pc[i]; r.la[2 * i] = u.x; r.la[2 * i + 1] = u.y; r.lc[2 * i] = v.x; r.lc[2 * i + 1] = v.y; }
-  const double* bn = w.bx(k + 1);
+  const double* bn = h.bx(k + 1);
 #pragma unroll
   for (int j = 0; j < 6; ++j) r.nb[j] = bn[j];
 }
-MPC_HD void chain_load_bwd(const View& w, int k, ChainRegs& r) {
-  const D2* __restrict__ pa = reinterpret_cast<const D2*>(w.blk(k));
+MPC_HD void chain_load_bwd(const HalfView& h, int k, ChainRegs& r) {
+  const D2* __restrict__ pa = reinterpret_cast<const D2*>(h.blk(k));
 #pragma unroll
   for (int i = 0; i < 11; ++i) { D2 u = pa[i], v = pa[11 + i]; r.la[2 * i] = u.x; r.la[2 * i + 1] = u.y; r.lc[2 * i] = v.x; r.lc[2 * i + 1] = v.y; }
-  const double* bp = w.bx(k - 1);
+  const double* bp = h.bx(k - 1);
 #pragma unroll
   for (int j = 0; j < 6; ++j) r.nb[j] = bp[j];
 }
@@ -514,66 +620,93 @@ MPC_HD void chain_math_bwd(const ChainRegs& r, double* a, double* out) {
 #pragma unroll
   for (int j = 0; j < 6; ++j) a[j] = nx[j];
 }
+MPC_HD void chain_store(double* bk, const double* out) {
+#pragma unroll
+  for (int j = 0; j < 6; ++j) bk[j] = out[j];
+}
 
-// Software-pipelined by hand (two register sets, loop unrolled by two): the loads of stage k+1 are issued
-// BEFORE the arithmetic and the stores of stage k, so that their latency hides under ~40 DFMAs; the
-// compiler cannot do this itself because it must assume the stores alias the next loads.
-MPC_HD void chain_solve(const View& w) {
-  const int N = w.N;
-  double a[6], out[6];
-  ChainRegs r0, r1;
-  // ---- forward: w = L^{-1} b, stored scaled by D^{-1} ----
+// Forward sweep of one half over its local stages 0..H-2; returns the accumulators of the border stage in a[].
+// PIPE = true: software-pipelined by hand (two register sets, loop unrolled by two): the loads of stage k+1 are
+// issued BEFORE the arithmetic and the stores of stage k (the compiler cannot do this itself because it must
+// assume the stores alias the next loads); ~190 registers.  PIPE = false: one register set (~80 registers).
+template <bool PIPE>
+MPC_HD void half_forward(const HalfView& h, double* a) {
+  const int last = h.H - 2;                 // last eliminated local stage
+  double out[6];
+  ChainRegs r0;
   {
-    const double* b0 = w.bx(0);
+    const double* b0 = h.bx(0);
 #pragma unroll
     for (int j = 0; j < 6; ++j) a[j] = b0[j];
-    chain_load_fwd(w, 0, r0);
+  }
+  if (PIPE) {
+    ChainRegs r1;
+    if (last >= 0) chain_load_fwd(h, 0, r0);
     int k = 0;
-    for (; k + 1 <= N; k += 2) {
-      chain_load_fwd(w, k + 1, r1);
+    for (; k + 1 <= last; k += 2) {
+      chain_load_fwd(h, k + 1, r1);
       chain_math_fwd(r0, a, out);
-      { double* bk = w.bx(k);
-#pragma unroll
-        for (int j = 0; j < 6; ++j) bk[j] = out[j]; }
-      if (k + 2 <= N) chain_load_fwd(w, k + 2, r0);
+      chain_store(h.bx(k), out);
+      if (k + 2 <= last) chain_load_fwd(h, k + 2, r0);
       chain_math_fwd(r1, a, out);
-      { double* bk = w.bx(k + 1);
-#pragma unroll
-        for (int j = 0; j < 6; ++j) bk[j] = out[j]; }
+      chain_store(h.bx(k + 1), out);
     }
-    if (k <= N) {
+    if (k <= last) {
       chain_math_fwd(r0, a, out);
-      double* bk = w.bx(k);
-#pragma unroll
-      for (int j = 0; j < 6; ++j) bk[j] = out[j];
+      chain_store(h.bx(k), out);
+    }
+  } else {
+    for (int k = 0; k <= last; ++k) {
+      chain_load_fwd(h, k, r0);
+      chain_math_fwd(r0, a, out);
+      chain_store(h.bx(k), out);
     }
   }
-  // ---- backward: x = L^{-T} (D^{-1} w) ----
-  {
-    const double* bN = w.bx(N);
+}
+// Backward sweep of one half from the border (whose solution xm, in the half's local index order, is given and
+// whose in-stage factor part is zero) down to local stage 0.
+template <bool PIPE>
+MPC_HD void half_backward(const HalfView& h, const double* xm) {
+  double a[6], out[6];
+  ChainRegs r0;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) a[j] = bN[j];
-    chain_load_bwd(w, N, r0);
-    int k = N;
+  for (int j = 0; j < 6; ++j) a[j] = xm[j];
+  const int first = h.H - 1;
+  if (PIPE) {
+    ChainRegs r1;
+    chain_load_bwd(h, first, r0);
+    int k = first;
     for (; k - 1 >= 0; k -= 2) {
-      chain_load_bwd(w, k - 1, r1);
+      chain_load_bwd(h, k - 1, r1);
       chain_math_bwd(r0, a, out);
-      { double* bk = w.bx(k);
-#pragma unroll
-        for (int j = 0; j < 6; ++j) bk[j] = out[j]; }
-      if (k - 2 >= 0) chain_load_bwd(w, k - 2, r0);
+      chain_store(h.bx(k), out);
+      if (k - 2 >= 0) chain_load_bwd(h, k - 2, r0);
       chain_math_bwd(r1, a, out);
-      { double* bk = w.bx(k - 1);
-#pragma unroll
-        for (int j = 0; j < 6; ++j) bk[j] = out[j]; }
+      chain_store(h.bx(k - 1), out);
     }
     if (k >= 0) {
       chain_math_bwd(r0, a, out);
-      double* bk = w.bx(k);
-#pragma unroll
-      for (int j = 0; j < 6; ++j) bk[j] = out[j];
+      chain_store(h.bx(k), out);
+    }
+  } else {
+    for (int k = first; k >= 0; --k) {
+      chain_load_bwd(h, k, r0);
+      chain_math_bwd(r0, a, out);
+      chain_store(h.bx(k), out);
     }
   }
+}
+// whole twisted solve, sequential (host emulation / single-lane use): L D L' x = b in place on the bx storage
+MPC_HD void chain_solve(const View& w) {
+  HalfView T = w.top(), B = w.bottom();
+  double aT[6], aB[6], xm[6], xr[6];
+  half_forward<false>(T, aT);
+  half_forward<false>(B, aB);
+  for (int j = 0; j < 6; ++j) aT[j] += aB[5 - j];
+  middle_solve(w, aT, xm);
+  for (int j = 0; j < 6; ++j) xr[j] = xm[5 - j];
+  half_backward<false>(T, xm);
+  half_backward<false>(B, xr);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -618,9 +751,8 @@ MPC_HD void admm_update_stage(const View& w, const Params& p, const Settings& s,
 // second half of A1: relax x (kept separate because A1 reads neighbours' x-tilde from bx, not state)
 MPC_HD void admm_relax_x_stage(const View& w, const Settings& s, int k) {
   double* rc = w.rec(k);
-  const double* b = w.bx(k);
   const int nj = k < w.N ? 6 : 4;
-  for (int j = 0; j < nj; ++j) rc[R_XU + j] = s.alpha * b[j] + (1.0 - s.alpha) * rc[R_XU + j];
+  for (int j = 0; j < nj; ++j) rc[R_XU + j] = s.alpha * w.bx_get(k, j) + (1.0 - s.alpha) * rc[R_XU + j];
 }
 
 // row provider for the ADMM rhs: value = rho_i z_i - y_i
@@ -653,13 +785,12 @@ MPC_HD void admm_rhs_stage(const View& w, const Params& p, const Settings& s, do
   }
   double out[6];
   gather_xu(w, p, k, rp, out);
-  double* b = w.bx(k);
   const int nj = k < N ? 6 : 4;
   for (int j = 0; j < nj; ++j) {
     double qj = j < 4 ? rc[R_Q + j] : 0.0;
-    b[j] = s.sigma * rc[R_XU + j] - qj + out[j];
+    w.bx_set(k, j, s.sigma * rc[R_XU + j] - qj + out[j]);
   }
-  for (int j = nj; j < 6; ++j) b[j] = 0.0;
+  for (int j = nj; j < 6; ++j) w.bx_set(k, j, 0.0);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -845,15 +976,14 @@ MPC_HD void polish_rhs_stage(const View& w, const Params& p, const Mode& m, int 
   }
   double out[6];
   gather_xu(w, p, k, rp, out);
-  double* b = w.bx(k);
   const double* qd = k < N ? p.q : p.qn;
   const int nj = k < N ? 6 : 4;
   for (int j = 0; j < nj; ++j) {
     double pd = j < 4 ? 2.0 * qd[j] : 2.0 * p.r[j - 4];
     double qj = j < 4 ? rc[R_Q + j] : 0.0;
-    b[j] = -qj - pd * rc[R_XU + j] + out[j];
+    w.bx_set(k, j, -qj - pd * rc[R_XU + j] + out[j]);
   }
-  for (int j = nj; j < 6; ++j) b[j] = 0.0;
+  for (int j = nj; j < 6; ++j) w.bx_set(k, j, 0.0);
 }
 // S3a(k): ds and dy from the banded correction; y += dy (row-owned); ds left in R_ST
 MPC_HD void polish_dual_stage(const View& w, const Params& p, const Mode& m, int k) {
@@ -892,9 +1022,8 @@ MPC_HD void polish_dual_stage(const View& w, const Params& p, const Mode& m, int
 // S3b(k): x += dx, s += ds
 MPC_HD void polish_primal_stage(const View& w, int k) {
   double* rc = w.rec(k);
-  const double* b = w.bx(k);
   const int nj = k < w.N ? 6 : 4;
-  for (int j = 0; j < nj; ++j) rc[R_XU + j] += b[j];
+  for (int j = 0; j < nj; ++j) rc[R_XU + j] += w.bx_get(k, j);
   const int ng = ngroups(w.N, k);
   for (int g = 0; g < ng; ++g) rc[R_S + g] += rc[R_ST + g];
 }

@@ -54,9 +54,9 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
     for (int i = 0; i < 4; ++i) h[H_X0 + i] = io.x0[i];
     for (int i = 0; i < 2; ++i) h[H_UPREV + i] = io.u_prev ? io.u_prev[i] : 0.0;
     for (int i = 0; i < N + 2; ++i) w.act()[i] = 0;
-    unwrap_window(io.ref, NS, w.bx(0));                   // scratch: bx area holds the unwrapped yaw column
+    unwrap_window(io.ref, NS, w.scratch());               // scratch: bx area holds the unwrapped yaw column
   });
-  ex.stages(NS, [&](int k) { setup_stage(w, p, k, io.ref, w.bx(0)); });
+  ex.stages(NS, [&](int k) { setup_stage(w, p, k, io.ref, w.scratch()); });
 
   // ---- initial iterate -------------------------------------------------------------------
   double rho = s.rho0;
