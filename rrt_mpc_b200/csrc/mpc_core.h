@@ -794,6 +794,159 @@ MPC_HD void admm_rhs_stage(const View& w, const Params& p, const Settings& s, do
 }
 
 // ----------------------------------------------------------------------------------------------
+// Specialised ADMM phases (the per-iteration hot code).  Same mathematics as admm_update_stage /
+// admm_relax_x_stage / admm_rhs_stage above (kept as the readable statement and used by nothing hot), with the
+// loops over groups and rows unrolled at compile time, bounds hoisted, one-sided clips instead of two-sided,
+// and v + alpha (z~ - z) in place of alpha z~ + (1-alpha) z + (v - z).
+// ----------------------------------------------------------------------------------------------
+struct IterConst {
+  double rho, rho_eq, alpha, sigma, ra;     // ra = rho_eq * alpha
+  double lo[5], hi[5], mssinv[5];           // soft-group bounds (stage k > 0) and 1 / (2w + sigma + 3 rho)
+  double up0, up1;                          // u_prev: shifts the rate bounds of stage 0
+};
+MPC_HD IterConst iter_const(const View& w, const Params& p, const Settings& s, double rho) {
+  IterConst c;
+  c.rho = rho; c.rho_eq = s.rho_eq_factor * rho; c.alpha = s.alpha; c.sigma = s.sigma; c.ra = c.rho_eq * s.alpha;
+  c.lo[0] = p.v_lo; c.hi[0] = p.v_hi;
+  c.lo[1] = p.u_lo[0]; c.hi[1] = p.u_hi[0]; c.lo[2] = p.u_lo[1]; c.hi[2] = p.u_hi[1];
+  c.lo[3] = p.du_lo[0]; c.hi[3] = p.du_hi[0]; c.lo[4] = p.du_lo[1]; c.hi[4] = p.du_hi[1];
+  c.mssinv[0] = 1.0 / (2.0 * p.w_v + s.sigma + 3.0 * rho);
+  c.mssinv[1] = c.mssinv[2] = 1.0 / (2.0 * p.w_u + s.sigma + 3.0 * rho);
+  c.mssinv[3] = c.mssinv[4] = 1.0 / (2.0 * p.w_du + s.sigma + 3.0 * rho);
+  c.up0 = w.hdr()[H_UPREV]; c.up1 = w.hdr()[H_UPREV + 1];
+  return c;
+}
+MPC_HD double dmin2(double a, double b) { return a < b ? a : b; }
+MPC_HD double dmax2(double a, double b) { return a > b ? a : b; }
+// pointer to the six entries of stage k in the twisted rhs/solution storage; rev: stored index-reversed
+MPC_HD double* bx_ptr(const View& w, int k, int& rev) {
+  const int m = mid_stage(w.N);
+  if (k <= m) { rev = 0; return w.top().bx(k); }
+  rev = 1; return w.bottom().bx(w.N - k);
+}
+MPC_HD void bx_load6(const View& w, int k, double* x) {
+  int rev; const double* b = bx_ptr(w, k, rev);
+  if (!rev) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) x[j] = b[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) x[j] = b[5 - j];
+  }
+}
+
+// A1: consume x-tilde / s-tilde, relax x and s, update the row states
+MPC_HD void admm_update_fast(const View& w, const Params& p, const IterConst& c, int k) {
+  const int N = w.N;
+  double* rc = w.rec(k);
+  double xt[6], xn[6], xp[6];
+  bx_load6(w, k, xt);
+  const bool reg = k < N;
+  if (reg) bx_load6(w, k + 1, xn);
+  double ua = 0.0, ud = 0.0;
+  if (k > 0 && reg) { bx_load6(w, k - 1, xp); ua = xp[4]; ud = xp[5]; }
+  const double off0 = k == 0 ? c.up0 : 0.0, off1 = k == 0 ? c.up1 : 0.0;
+  const double gt[5] = {xt[3], xt[4], xt[5], xt[4] - ua, xt[5] - ud};
+  const double offs[5] = {0.0, 0.0, 0.0, off0, off1};
+#pragma unroll
+  for (int g = 0; g < 5; ++g) {
+    if (g == 0 || reg) {
+      const double st = rc[R_ST + g], sv = rc[R_S + g];
+      const double v0 = rc[R_V + 3 * g], v1 = rc[R_V + 3 * g + 1], v2 = rc[R_V + 3 * g + 2];
+      const double z0 = dmin2(v0, c.hi[g] + offs[g]), z1 = dmax2(v1, c.lo[g] + offs[g]), z2 = dmax2(v2, 0.0);
+      rc[R_V + 3 * g] = fma(c.alpha, (gt[g] - st) - z0, v0);
+      rc[R_V + 3 * g + 1] = fma(c.alpha, (gt[g] + st) - z1, v1);
+      rc[R_V + 3 * g + 2] = fma(c.alpha, st - z2, v2);
+      rc[R_S + g] = fma(c.alpha, st - sv, sv);
+    }
+  }
+  if (reg) {
+    const double* lin = rc + R_LIN;
+    const double z0 = xn[0] - (xt[0] + lin[0] * xt[2] + lin[1] * xt[3]);
+    const double z1 = xn[1] - (xt[1] + lin[2] * xt[2] + lin[3] * xt[3]);
+    const double z2 = xn[2] - (xt[2] + lin[4] * xt[5]);
+    const double z3 = xn[3] - (xt[3] + p.dt * xt[4]);
+    rc[R_YE + 0] = fma(c.ra, z0 - lin[5], rc[R_YE + 0]);
+    rc[R_YE + 1] = fma(c.ra, z1 - lin[6], rc[R_YE + 1]);
+    rc[R_YE + 2] = fma(c.ra, z2, rc[R_YE + 2]);
+    rc[R_YE + 3] = fma(c.ra, z3, rc[R_YE + 3]);
+  }
+  if (k == 0) {
+    double* h = w.hdr();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) h[H_YI + r] = fma(c.ra, xt[r] - h[H_X0 + r], h[H_YI + r]);
+  }
+#pragma unroll
+  for (int j = 0; j < 6; ++j)
+    if (j < 4 || reg) { const double xo = rc[R_XU + j]; rc[R_XU + j] = fma(c.alpha, xt[j] - xo, xo); }
+}
+
+// A2: t = rho z - y of every row from the new state, s-tilde, banded right-hand side
+MPC_HD void admm_rhs_fast(const View& w, const Params& p, const IterConst& c, int k) {
+  const int N = w.N;
+  double* rc = w.rec(k);
+  const bool reg = k < N;
+  const double off0 = k == 0 ? c.up0 : 0.0, off1 = k == 0 ? c.up1 : 0.0;
+  const double offs[5] = {0.0, 0.0, 0.0, off0, off1};
+  double G[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int g = 0; g < 5; ++g) {
+    if (g == 0 || reg) {
+      const double v0 = rc[R_V + 3 * g], v1 = rc[R_V + 3 * g + 1], v2 = rc[R_V + 3 * g + 2];
+      const double z0 = dmin2(v0, c.hi[g] + offs[g]), z1 = dmax2(v1, c.lo[g] + offs[g]), z2 = dmax2(v2, 0.0);
+      const double t0 = c.rho * (z0 + (z0 - v0)), t1 = c.rho * (z1 + (z1 - v1)), t2 = c.rho * (z2 + (z2 - v2));
+      rc[R_ST + g] = (c.sigma * rc[R_S + g] + ((t1 - t0) + t2)) * c.mssinv[g];
+      G[g] = t0 + t1;
+    }
+  }
+  double out[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (k >= 1) {
+    const double* rp = w.rec(k - 1);
+    out[0] = c.rho_eq * rp[R_LIN + 5] - rp[R_YE + 0];
+    out[1] = c.rho_eq * rp[R_LIN + 6] - rp[R_YE + 1];
+    out[2] = -rp[R_YE + 2];
+    out[3] = -rp[R_YE + 3];
+  } else {
+    const double* h = w.hdr();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) out[r] = c.rho_eq * h[H_X0 + r] - h[H_YI + r];
+  }
+  out[3] += G[0];
+  if (reg) {
+    const double* lin = rc + R_LIN;
+    const double d0 = c.rho_eq * lin[5] - rc[R_YE + 0], d1 = c.rho_eq * lin[6] - rc[R_YE + 1];
+    const double d2 = -rc[R_YE + 2], d3 = -rc[R_YE + 3];
+    out[0] -= d0;
+    out[1] -= d1;
+    out[2] -= lin[0] * d0 + lin[2] * d1 + d2;
+    out[3] -= lin[1] * d0 + lin[3] * d1 + d3;
+    out[4] = G[1] + G[3] - p.dt * d3;
+    out[5] = G[2] + G[4] - lin[4] * d2;
+    if (k + 1 < N) {
+      const double* rn = w.rec(k + 1);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const double v0 = rn[R_V + 3 * (3 + i)], v1 = rn[R_V + 3 * (3 + i) + 1];
+        const double z0 = dmin2(v0, c.hi[3 + i]), z1 = dmax2(v1, c.lo[3 + i]);
+        out[4 + i] -= c.rho * (z0 + (z0 - v0)) + c.rho * (z1 + (z1 - v1));
+      }
+    }
+  }
+  int rev; double* b = bx_ptr(w, k, rev);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double val = 0.0;
+    if (j < 4 || reg) val = c.sigma * rc[R_XU + j] - (j < 4 ? rc[R_Q + j] : 0.0) + out[j];
+    b[rev ? 5 - j : j] = val;
+  }
+  if (k == mid_stage(N)) {
+    double* bb = w.bottom().bx(N - k);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) bb[j] = 0.0;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // Residuals of the current iterate (x, z = clip(v), y): per-stage partial maxima
 //   r[0] |Ax - z|, r[1] |Ax|, r[2] |z|, r[3] |Px + q + A'y|, r[4] |Px|, r[5] |A'y|, r[6] |q|
 // mode 0: ADMM state (R_V holds v);  mode 1: polished state (R_V holds y, z := clip(Ax))

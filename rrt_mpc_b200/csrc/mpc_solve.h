@@ -71,7 +71,8 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
   Mode mode = admm_mode(rho, s);
   ex.stages(NS, [&](int k) { assemble_stage(w, p, mode, k); });
   ex.factor(w); ++n_fac;
-  ex.stages(NS, [&](int k) { admm_rhs_stage(w, p, s, rho, k); });
+  IterConst ic = iter_const(w, p, s, rho);
+  ex.stages(NS, [&](int k) { admm_rhs_fast(w, p, ic, k); });
 
   // ---- ADMM + polish; a rejected polish (wrong active set) resumes ADMM at a 10x tighter internal tolerance ----
   int status = STATUS_UNSOLVED;
@@ -84,7 +85,7 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
     while (it < s.max_iter) {
       ++it;
       ex.tag(1); ex.solve(w); ++n_solve;
-      ex.tag(2); ex.stages(NS, [&](int k) { admm_update_stage(w, p, s, rho, k); admm_relax_x_stage(w, s, k); });
+      ex.tag(2); ex.stages(NS, [&](int k) { admm_update_fast(w, p, ic, k); });
       const bool check = (s.check_termination > 0) && (it % s.check_termination == 0);
       const bool adapt = s.adaptive_rho && (s.adaptive_rho_interval > 0) && (it % s.adaptive_rho_interval == 0);
       if (check || adapt) {
@@ -99,10 +100,11 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
             mode = admm_mode(rho, s);
             ex.tag(4); ex.stages(NS, [&](int k) { assemble_stage(w, p, mode, k); });
             ex.tag(5); ex.factor(w); ++n_fac;
+            ic = iter_const(w, p, s, rho);
           }
         }
       }
-      ex.tag(6); ex.stages(NS, [&](int k) { admm_rhs_stage(w, p, s, rho, k); });
+      ex.tag(6); ex.stages(NS, [&](int k) { admm_rhs_fast(w, p, ic, k); });
     }
     ex.tag(7);
     if (attempt == 0) {
@@ -177,7 +179,7 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
     se.eps_abs *= 0.1; se.eps_rel *= 0.1;
     ex.stages(NS, [&](int k) { assemble_stage(w, p, mode, k); });      // the polish factor replaced the ADMM factor
     ex.factor(w); ++n_fac;
-    ex.stages(NS, [&](int k) { admm_rhs_stage(w, p, s, rho, k); });
+    ex.stages(NS, [&](int k) { admm_rhs_fast(w, p, ic, k); });
   }
 
   // ---- outputs (mpc_controller.py:141: U[:,0], X (4,N+1), U (2,N)) --------------------------
