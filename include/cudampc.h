@@ -85,6 +85,9 @@ typedef struct cudampc_settings {
   int32_t warm_start;            /* 1: start from the iterate this handle stored for the same slot in the last call */
   int32_t polish_retry;          /* if OSQP's polish is rejected (active set not identified): resume ADMM at a 10x tighter
                                     internal tolerance and polish again, up to this many times (0 = OSQP behaviour) */
+  int32_t early_polish;          /* 1: also try the polish at termination checks whose guessed active set repeated; a polish that
+                                    ends on a KKT point of a settled active set finishes the solve early (0 = OSQP behaviour) */
+  int32_t early_polish_start;    /* first iteration for such a try (default 50) */
 } cudampc_settings;
 
 /* Closed-loop constants of TrajectoryTracker.track (control_stage.py:84,141-150) */

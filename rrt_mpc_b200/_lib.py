@@ -22,7 +22,8 @@ class Settings(C.Structure):
                 ("rho_min", C.c_double), ("rho_max", C.c_double), ("delta", C.c_double),
                 ("max_iter", C.c_int32), ("check_termination", C.c_int32), ("adaptive_rho", C.c_int32),
                 ("adaptive_rho_interval", C.c_int32), ("polish_passes", C.c_int32), ("polish_refine_iter", C.c_int32),
-                ("warm_start", C.c_int32), ("polish_retry", C.c_int32)]
+                ("warm_start", C.c_int32), ("polish_retry", C.c_int32),
+                ("early_polish", C.c_int32), ("early_polish_start", C.c_int32)]
 
 
 class RolloutCfg(C.Structure):

@@ -308,6 +308,7 @@ static int convert_settings(const cudampc_settings* in, Settings* s, cudampc_han
   s->adaptive_rho_interval = in->adaptive_rho_interval; s->polish_passes = in->polish_passes;
   s->polish_refine_iter = in->polish_refine_iter; s->warm_start = in->warm_start;
   s->polish_retry = in->polish_retry < 0 ? 0 : in->polish_retry;
+  s->early_polish = in->early_polish; s->early_polish_start = in->early_polish_start;
   return CUDAMPC_OK;
 }
 
@@ -322,6 +323,7 @@ void cudampc_default_settings(cudampc_settings* s) {
   s->sigma = 1e-6; s->adaptive_rho_tolerance = 5.0; s->rho_eq_factor = 1e3; s->rho_min = 1e-6; s->rho_max = 1e6;
   s->delta = 1e-6; s->max_iter = 60000; s->check_termination = 25; s->adaptive_rho = 1; s->adaptive_rho_interval = 50;
   s->polish_passes = 1; s->polish_refine_iter = 3; s->warm_start = 0; s->polish_retry = 0;
+  s->early_polish = 0; s->early_polish_start = 50;
 }
 
 void cudampc_default_rollout_cfg(cudampc_rollout_cfg* c) {

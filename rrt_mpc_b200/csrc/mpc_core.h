@@ -49,6 +49,8 @@ struct Settings {
   int max_iter, check_termination, adaptive_rho, adaptive_rho_interval;
   int polish_passes, polish_refine_iter, warm_start;
   int polish_retry;   // resume ADMM at a tighter internal tolerance this many times if the polish is rejected
+  int early_polish;        // try the polish at termination checks whose guessed active set repeated (0 = OSQP)
+  int early_polish_start;  // first iteration at which an early polish may be tried
 };
 
 enum { STATUS_SOLVED = 1, STATUS_SOLVED_INACCURATE = 2, STATUS_MAX_ITER = -2, STATUS_UNSOLVED = -10 };
@@ -1076,6 +1078,33 @@ MPC_HD int polish_activity_stage(const View& w, const Params& p, double rho, int
     for (int r = 0; r < 4; ++r) ib |= (w.hdr()[H_YI + r] != 0.0) << r;
     changed |= (w.act()[N + 1] != ib);
     w.act()[N + 1] = ib;
+  }
+  return changed;
+}
+
+// Active set the ADMM pair (z, y) suggests right now (upper-active u - z < y <=> v > hi, ...), WITHOUT touching the
+// state: stores it in act[] and reports whether it differs from the stored one.
+MPC_HD int activity_probe_stage(const View& w, const Params& p, int k) {
+  const int N = w.N;
+  const double* rc = w.rec(k);
+  const int old = w.act()[k];
+  int bits = 0;
+  const int ng = ngroups(N, k);
+  const double tol = 1e-6;       // rows closer than this to their bound (weakly active, round-off decides) keep their bit
+  for (int g = 0; g < ng; ++g) {
+    double lo, hi; group_bounds(p, w.hdr(), k, g, lo, hi);
+    const double m0 = rc[R_V + 3 * g] - hi, m1 = lo - rc[R_V + 3 * g + 1], m2 = -rc[R_V + 3 * g + 2];
+    const int b0 = fabs(m0) <= tol ? (old >> (3 * g)) & 1 : (m0 > 0.0);
+    const int b1 = fabs(m1) <= tol ? (old >> (3 * g + 1)) & 1 : (m1 > 0.0);
+    const int b2 = fabs(m2) <= tol ? (old >> (3 * g + 2)) & 1 : (m2 > 0.0);
+    bits |= (b0 << (3 * g)) | (b1 << (3 * g + 1)) | (b2 << (3 * g + 2));
+  }
+  if (k < N) bits |= 0xF << 15;      // equality rows are always active
+  int changed = (old != bits);
+  w.act()[k] = bits;
+  if (k == 0) {
+    changed |= (w.act()[N + 1] != 0xF);
+    w.act()[N + 1] = 0xF;
   }
   return changed;
 }

@@ -74,68 +74,40 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
   IterConst ic = iter_const(w, p, s, rho);
   ex.stages(NS, [&](int k) { admm_rhs_fast(w, p, ic, k); });
 
-  // ---- ADMM + polish; a rejected polish (wrong active set) resumes ADMM at a 10x tighter internal tolerance ----
+  // ---- ADMM + polish --------------------------------------------------------------------------
+  // OSQP: iterate until the residual test passes, then polish once.  Two opt-in extensions:
+  //  * polish_retry: a polish that is rejected or does not end on a KKT point (active set not identified) restores
+  //    the ADMM iterate, tightens the internal tolerance 10x and iterates on;
+  //  * early_polish: at a termination check whose guessed active set equals the one of the previous check, the
+  //    polish is tried although the residual test has not passed yet; if it ends on a KKT point of a settled active
+  //    set (sufficient for optimality of this strictly convex QP) the solve is finished, otherwise ADMM resumes.
   int status = STATUS_UNSOLVED;
   int it = 0;
   Residuals res; res.pri = res.dua = 1e300; res.eps_p = res.eps_d = 0.0; res.sp = res.sd = 0.0; res.nz = res.nq = 0.0;
   double pri = 1e300, dua = 1e300;
-  Settings se = s;                         // effective tolerances of the current attempt
-  for (int attempt = 0; attempt <= s.polish_retry; ++attempt) {
-    bool converged = false;
-    while (it < s.max_iter) {
-      ++it;
-      ex.tag(1); ex.solve(w); ++n_solve;
-      ex.tag(2); ex.stages(NS, [&](int k) { admm_update_fast(w, p, ic, k); });
-      const bool check = (s.check_termination > 0) && (it % s.check_termination == 0);
-      const bool adapt = s.adaptive_rho && (s.adaptive_rho_interval > 0) && (it % s.adaptive_rho_interval == 0);
-      if (check || adapt) {
-        ex.tag(3); res = compute_residuals(ex, w, p, se, rho, 0);
-        if (check && res.pri <= res.eps_p && res.dua <= res.eps_d) { converged = true; break; }
-        if (adapt) {
-          double rho_new = rho * sqrt(res.sp / (res.sd + 1e-10));
-          rho_new = fmin(fmax(rho_new, s.rho_min), s.rho_max);
-          if (rho_new > rho * s.adaptive_rho_tolerance || rho_new < rho / s.adaptive_rho_tolerance) {
-            ex.stages(NS, [&](int k) { rescale_v_stage(w, p, rho, rho_new, k); });
-            rho = rho_new; ++n_rho;
-            mode = admm_mode(rho, s);
-            ex.tag(4); ex.stages(NS, [&](int k) { assemble_stage(w, p, mode, k); });
-            ex.tag(5); ex.factor(w); ++n_fac;
-            ic = iter_const(w, p, s, rho);
-          }
-        }
-      }
-      ex.tag(6); ex.stages(NS, [&](int k) { admm_rhs_fast(w, p, ic, k); });
-    }
-    ex.tag(7);
-    if (attempt == 0) {
-      if (converged) status = STATUS_SOLVED;
-      else {
-        res = compute_residuals(ex, w, p, s, rho, 0);
-        if (res.pri <= res.eps_p && res.dua <= res.eps_d) status = STATUS_SOLVED;
-        else {
-          double ep10 = 10.0 * s.eps_abs + 10.0 * (res.eps_p - s.eps_abs);
-          double ed10 = 10.0 * s.eps_abs + 10.0 * (res.eps_d - s.eps_abs);
-          status = (res.pri <= ep10 && res.dua <= ed10) ? STATUS_SOLVED_INACCURATE : STATUS_MAX_ITER;
-        }
-      }
-    } else if (!converged) {
-      res = compute_residuals(ex, w, p, se, rho, 0);
-    }
-    pri = res.pri; dua = res.dua;
+  Settings se = s;                         // effective tolerances (tightened by polish_retry)
+  int retries = s.polish_retry;
+  const bool can_polish = s.polish_passes > 0 && io.warm && io.scratch;
 
-    // keep the ADMM iterate in HBM (warm start of the next call; polish back-up)
-    if (io.warm) {
-      ex.stages(NS, [&](int k) { save_stage(w, k, io.warm); });
-      ex.single([&]() {
-        for (int r = 0; r < 4; ++r) io.warm[30 * NS + r] = w.hdr()[H_YI + r];
-        io.warm[30 * NS + 4] = rho;
-      });
-    }
-    if (!(status == STATUS_SOLVED && s.polish_passes > 0 && io.warm && io.scratch)) break;
-
-    // polish (OSQP polish = pass 1; further passes re-identify the active set from Ax + y)
+  auto save_iterate = [&]() {
+    ex.stages(NS, [&](int k) { save_stage(w, k, io.warm); });
+    ex.single([&]() {
+      for (int r = 0; r < 4; ++r) io.warm[30 * NS + r] = w.hdr()[H_YI + r];
+      io.warm[30 * NS + 4] = rho;
+    });
+  };
+  auto restore_iterate = [&](const double* src) {
+    ex.stages(NS, [&](int k) { load_stage(w, k, src); });
+    ex.single([&]() { for (int r = 0; r < 4; ++r) w.hdr()[H_YI + r] = src[30 * NS + r]; });
+  };
+  // Polish from the ADMM iterate in shared memory (which must already be saved in io.warm).  Returns true if it ended on
+  // a KKT point of a settled active set ("clean").  On return the state holds the last accepted polished pair
+  // (n_pol > 0) or the restored ADMM iterate (n_pol == 0); pri/dua are updated accordingly.
+  auto polish = [&](double pri0, double dua0) -> bool {
     const Mode pm = polish_mode(s);
-    bool settled = false;                  // the active set stopped changing (or only one pass was asked for)
+    bool settled = false;
+    int acc = 0, rejected = 0;
+    double pp = pri0, dd = dua0;
     for (int pass = 0; pass < s.polish_passes; ++pass) {
       if (pass > 0) {
         ex.stages(NS, [&](int k) { save_stage(w, k, io.scratch); });
@@ -155,32 +127,90 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
       Residuals rp = compute_residuals(ex, w, p, s, rho, 1);
       bool ok;
       if (pass == 0) {
-        ok = (rp.pri < pri && rp.dua < dua) || (rp.pri < pri && dua < 1e-10) || (rp.dua < dua && pri < 1e-10);
+        ok = (rp.pri < pp && rp.dua < dd) || (rp.pri < pp && dd < 1e-10) || (rp.dua < dd && pp < 1e-10);
       } else {
-        ok = rp.pri <= dmax(10.0 * pri, 1e-9 * dmax(1.0, res.nz)) && rp.dua <= dmax(10.0 * dua, 1e-9 * dmax(1.0, res.nq));
+        ok = rp.pri <= dmax(10.0 * pp, 1e-9 * dmax(1.0, res.nz)) && rp.dua <= dmax(10.0 * dd, 1e-9 * dmax(1.0, res.nq));
       }
-      if (ok) { pri = rp.pri; dua = rp.dua; n_pol = pass + 1; }
-      else {
-        const double* src = pass == 0 ? io.warm : io.scratch;
-        ex.stages(NS, [&](int k) { load_stage(w, k, src); });
-        ex.single([&]() { for (int r = 0; r < 4; ++r) w.hdr()[H_YI + r] = src[30 * NS + r]; });
-        break;
-      }
+      if (ok) { pp = rp.pri; dd = rp.dua; acc = pass + 1; }
+      else { rejected = pass == 0 ? 1 : 2; break; }
     }
-    // a clean polish solves the KKT system of a settled active set to round-off
-    const bool clean = n_pol > 0 && (settled || s.polish_passes == 1) &&
-                       pri <= 1e-9 * dmax(1.0, res.nz) && dua <= 1e-9 * dmax(1.0, res.nq);
-    if (clean || attempt == s.polish_retry || it >= s.max_iter) break;
-    // active set not identified (polish rejected, still changing, or left a residual): back to the ADMM iterate,
-    // tighten the internal tolerance and iterate on
+    if (rejected == 2) {               // a later pass was rejected: back to the previous accepted polished pair
+      ex.stages(NS, [&](int k) { load_stage(w, k, io.scratch); });
+      ex.single([&]() { for (int r = 0; r < 4; ++r) w.hdr()[H_YI + r] = io.scratch[30 * NS + r]; });
+    }
+    if (acc > 0) { pri = pp; dua = dd; }
+    n_pol = acc;
+    return acc > 0 && (settled || s.polish_passes == 1) && pp <= 1e-9 * dmax(1.0, res.nz) && dd <= 1e-9 * dmax(1.0, res.nq);
+  };
+  auto resume_admm = [&]() {               // the polish replaced the factor and (maybe) the state
     n_pol = 0;
     ex.stages(NS, [&](int k) { load_stage(w, k, io.warm); });
     ex.single([&]() { for (int r = 0; r < 4; ++r) w.hdr()[H_YI + r] = io.warm[30 * NS + r]; });
-    se.eps_abs *= 0.1; se.eps_rel *= 0.1;
-    ex.stages(NS, [&](int k) { assemble_stage(w, p, mode, k); });      // the polish factor replaced the ADMM factor
+    ex.stages(NS, [&](int k) { assemble_stage(w, p, mode, k); });
     ex.factor(w); ++n_fac;
-    ex.stages(NS, [&](int k) { admm_rhs_fast(w, p, ic, k); });
+  };
+
+  // NOTE: every multi-statement lambda above has exactly ONE call site below, so that it is inlined and the solver
+  // state it captures stays in registers (a second call site makes nvcc outline it and spill the captures to local memory).
+  bool finished = false, need_restore = false;
+  while (!finished) {
+    ++it;
+    ex.tag(1); ex.solve(w); ++n_solve;
+    ex.tag(2); ex.stages(NS, [&](int k) { admm_update_fast(w, p, ic, k); });
+    const bool last = it >= s.max_iter;
+    const bool check = last || ((s.check_termination > 0) && (it % s.check_termination == 0));
+    const bool adapt = !last && s.adaptive_rho && (s.adaptive_rho_interval > 0) && (it % s.adaptive_rho_interval == 0);
+    if (check || adapt) {
+      ex.tag(3); res = compute_residuals(ex, w, p, se, rho, 0);
+      pri = res.pri; dua = res.dua;
+      if (check) {
+        const bool converged = res.pri <= res.eps_p && res.dua <= res.eps_d;
+        if (converged && status == STATUS_UNSOLVED) status = STATUS_SOLVED;
+        if (last && status == STATUS_UNSOLVED) {
+          // iteration limit: OSQP's "solved inaccurate" test with 10x looser tolerances (user eps, not the tightened ones)
+          const double ep10 = 10.0 * s.eps_abs + 10.0 * s.eps_rel * res.nz, ed10 = 10.0 * s.eps_abs + 10.0 * s.eps_rel * res.nq;
+          status = (res.pri <= ep10 && res.dua <= ed10) ? STATUS_SOLVED_INACCURATE : STATUS_MAX_ITER;
+        }
+        bool attempt = converged || (last && status == STATUS_SOLVED);
+        if (!attempt && !last && s.early_polish && can_polish) {
+          const int changed = ex.any(NS, [&](int k) { return activity_probe_stage(w, p, k); });
+          attempt = (!changed || s.early_polish >= 2) && it >= s.early_polish_start;
+        }
+        if (attempt || last) {
+          if (io.warm) save_iterate();
+          if (attempt && can_polish) {
+            const bool clean = polish(res.pri, res.dua);
+            if (clean) { status = STATUS_SOLVED; finished = true; }
+            else if (last || (converged && retries <= 0)) {                      // keep what the polish gave (OSQP behaviour)
+              finished = true;
+              if (n_pol == 0) need_restore = true;
+            }
+            else {
+              if (converged) { --retries; se.eps_abs *= 0.1; se.eps_rel *= 0.1; }
+              resume_admm();
+            }
+          } else {
+            finished = true;
+          }
+        }
+      }
+      if (adapt && !finished) {
+        double rho_new = rho * sqrt(res.sp / (res.sd + 1e-10));
+        rho_new = fmin(fmax(rho_new, s.rho_min), s.rho_max);
+        if (rho_new > rho * s.adaptive_rho_tolerance || rho_new < rho / s.adaptive_rho_tolerance) {
+          ex.stages(NS, [&](int k) { rescale_v_stage(w, p, rho, rho_new, k); });
+          rho = rho_new; ++n_rho;
+          mode = admm_mode(rho, s);
+          ex.tag(4); ex.stages(NS, [&](int k) { assemble_stage(w, p, mode, k); });
+          ex.tag(5); ex.factor(w); ++n_fac;
+          ic = iter_const(w, p, s, rho);
+        }
+      }
+    }
+    if (!finished) { ex.tag(6); ex.stages(NS, [&](int k) { admm_rhs_fast(w, p, ic, k); }); }
   }
+  ex.tag(7);
+  if (need_restore) restore_iterate(io.warm);   // polish rejected outright: the answer is the ADMM iterate
 
   // ---- outputs (mpc_controller.py:141: U[:,0], X (4,N+1), U (2,N)) --------------------------
   ex.stages(NS, [&](int k) {

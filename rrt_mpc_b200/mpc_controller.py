@@ -64,6 +64,8 @@ class SolverSettings:
     polish_refine_iter: int = 3
     warm_start: bool = False      # upstream's warm_start=True is a no-op (a new Problem per call)
     polish_retry: int = 0         # rejected polish -> resume ADMM at 10x tighter internal eps, polish again (0 = OSQP)
+    early_polish: bool = False    # try the polish as soon as the guessed active set repeats; finish if it certifies a KKT point
+    early_polish_start: int = 50
 
     def to_c(self) -> _lib.Settings:
         lib = _lib.load()
@@ -76,6 +78,7 @@ class SolverSettings:
         s.adaptive_rho_tolerance, s.delta = self.adaptive_rho_tolerance, self.delta
         s.polish_refine_iter, s.warm_start = int(self.polish_refine_iter), int(self.warm_start)
         s.polish_retry = int(self.polish_retry)
+        s.early_polish, s.early_polish_start = int(self.early_polish), int(self.early_polish_start)
         return s
 
 

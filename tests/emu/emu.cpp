@@ -58,7 +58,7 @@ static void unpack(const double* par, const double* set, int N, Params& p, Setti
   s.delta = set[i++];
   s.max_iter = (int)set[i++]; s.check_termination = (int)set[i++]; s.adaptive_rho = (int)set[i++];
   s.adaptive_rho_interval = (int)set[i++]; s.polish_passes = (int)set[i++]; s.polish_refine_iter = (int)set[i++];
-  s.warm_start = (int)set[i++]; s.polish_retry = (int)set[i++];
+  s.warm_start = (int)set[i++]; s.polish_retry = (int)set[i++]; s.early_polish = (int)set[i++]; s.early_polish_start = (int)set[i++];
 }
 
 int emu_solve_batch(const double* par, const double* set, int N, int B, int reverse,

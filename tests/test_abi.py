@@ -30,7 +30,7 @@ def test_struct_layouts_and_defaults():
     from rrt_mpc_b200 import _lib
     lib = _lib.load()
     assert C.sizeof(_lib.Params) == 8 * 2 + 8 + 8 * (16 + 4 + 16 + 4 + 2 + 4 + 3)
-    assert C.sizeof(_lib.Settings) == 8 * 10 + 4 * 8
+    assert C.sizeof(_lib.Settings) == 8 * 10 + 4 * 10
     assert C.sizeof(_lib.RolloutCfg) == 8 + 8 * 5
     s = _lib.Settings()
     lib.cudampc_default_settings(C.byref(s))

@@ -29,7 +29,7 @@ def test_full_size_batches(N, B, du, seed):
     from rrt_mpc_b200.synthetic import make_batch
     from oracle import mpc_numpy as O
     x0, ref, up = make_batch(B, N, seed)
-    ctl = MPCController(product_params(N, du), SolverSettings(polish_passes=3, polish_retry=2, **TIGHT), max_batch=B)
+    ctl = MPCController(product_params(N, du), SolverSettings(polish_passes=5, polish_retry=2, early_polish=True, **TIGHT), max_batch=B)
     d = lambda a: torch.as_tensor(a).cuda()
     dx0, dref, dup = d(x0), d(ref), d(up)
     rd = ctl.solve_batch(dx0, dref, u_prev=dup)

@@ -40,7 +40,7 @@ int main(int argc, char** argv) {
   p.du_lo[0] = -12; p.du_hi[0] = 12; p.du_lo[1] = -0.02; p.du_hi[1] = 0.02; p.w_v = 1e3; p.w_u = 5e2; p.w_du = 5e2;
   Settings s; s.eps_abs = s.eps_rel = 1e-6; s.rho0 = 0.1; s.alpha = 1.6; s.sigma = 1e-6; s.adaptive_rho_tolerance = 5; s.rho_eq_factor = 1e3;
   s.rho_min = 1e-6; s.rho_max = 1e6; s.delta = 1e-6; s.max_iter = 60000; s.check_termination = 25; s.adaptive_rho = 1; s.adaptive_rho_interval = 50;
-  s.polish_passes = 3; s.polish_refine_iter = 3; s.warm_start = 0; s.polish_retry = 0;
+  s.polish_passes = 3; s.polish_refine_iter = 3; s.warm_start = 0; s.polish_retry = 0; s.early_polish = 0; s.early_polish_start = 50;
   std::vector<double> ref(4 * (N + 1)), x0(4), up(2, 0.0);
   for (int k2 = 0; k2 <= N; ++k2) { double th = 0.03 * k2; ref[4 * k2] = 100 + 2 * k2 * cos(0.3 + th / 2); ref[4 * k2 + 1] = 100 + 2 * k2 * sin(0.3 + th / 2); ref[4 * k2 + 2] = 0.3 + th; ref[4 * k2 + 3] = 14.0; }
   x0[0] = 101; x0[1] = 99; x0[2] = 0.35; x0[3] = 12; up[0] = 1.0; up[1] = 0.05;
