@@ -804,6 +804,7 @@ MPC_HD void admm_rhs_stage(const View& w, const Params& p, const Settings& s, do
 struct IterConst {
   double rho, rho_eq, alpha, sigma, ra;     // ra = rho_eq * alpha
   double lo[5], hi[5], mssinv[5];           // soft-group bounds (stage k > 0) and 1 / (2w + sigma + 3 rho)
+  double ps_[5];                            // P entries of the slacks (2w)
   double up0, up1;                          // u_prev: shifts the rate bounds of stage 0
 };
 MPC_HD IterConst iter_const(const View& w, const Params& p, const Settings& s, double rho) {
@@ -815,6 +816,7 @@ MPC_HD IterConst iter_const(const View& w, const Params& p, const Settings& s, d
   c.mssinv[0] = 1.0 / (2.0 * p.w_v + s.sigma + 3.0 * rho);
   c.mssinv[1] = c.mssinv[2] = 1.0 / (2.0 * p.w_u + s.sigma + 3.0 * rho);
   c.mssinv[3] = c.mssinv[4] = 1.0 / (2.0 * p.w_du + s.sigma + 3.0 * rho);
+  for (int g = 0; g < 5; ++g) c.ps_[g] = group_ps(p, g);
   c.up0 = w.hdr()[H_UPREV]; c.up1 = w.hdr()[H_UPREV + 1];
   return c;
 }
@@ -1216,6 +1218,288 @@ MPC_HD void polish_zero_stage(const View& w, int k) {
   for (int j = 0; j < 15; ++j) rc[R_V + j] = 0.0;
   for (int r = 0; r < 4; ++r) rc[R_YE + r] = 0.0;
   if (k == 0) for (int r = 0; r < 4; ++r) w.hdr()[H_YI + r] = 0.0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Specialised polish / residual phases: same mathematics as polish_rhs_stage, polish_dual_stage and
+// residual_stage above (kept as the readable statement), unrolled at compile time, with the slack-elimination
+// coefficients tabulated per (group type, number of active rows) instead of divided out per use.
+// ----------------------------------------------------------------------------------------------
+struct PolConst {
+  double invd;
+  double lo[5], hi[5], ps[5];
+  double mssinv[5][4];      // delta / ((ps + delta) delta + na), na = number of active rows of the group
+  double up0, up1;
+};
+MPC_HD PolConst pol_const(const View& w, const Params& p, const Settings& s) {
+  PolConst c;
+  c.invd = 1.0 / s.delta;
+  c.lo[0] = p.v_lo; c.hi[0] = p.v_hi;
+  c.lo[1] = p.u_lo[0]; c.hi[1] = p.u_hi[0]; c.lo[2] = p.u_lo[1]; c.hi[2] = p.u_hi[1];
+  c.lo[3] = p.du_lo[0]; c.hi[3] = p.du_hi[0]; c.lo[4] = p.du_lo[1]; c.hi[4] = p.du_hi[1];
+  for (int g = 0; g < 5; ++g) {
+    c.ps[g] = group_ps(p, g);
+    for (int na = 0; na < 4; ++na) c.mssinv[g][na] = s.delta / ((c.ps[g] + s.delta) * s.delta + na);
+  }
+  c.up0 = w.hdr()[H_UPREV]; c.up1 = w.hdr()[H_UPREV + 1];
+  return c;
+}
+MPC_HD double mss_pick(const PolConst& c, int g, int bits) {
+  const int na = (bits & 1) + ((bits >> 1) & 1) + ((bits >> 2) & 1);
+  return na == 0 ? c.mssinv[g][0] : (na == 1 ? c.mssinv[g][1] : (na == 2 ? c.mssinv[g][2] : c.mssinv[g][3]));
+}
+// value_i = act_i (e2_i / delta - y_i) of the three rows of one soft group; returns the pair-combined value after
+// eliminating the slack and the reduced slack rhs
+MPC_HD double pol_group_val(const PolConst& c, int g, int bits, double gv, double sv, double lo, double hi,
+                            double y0, double y1, double y2, double& rr_s) {
+  const double v0 = (bits & 1) ? fma(hi - (gv - sv), c.invd, -y0) : 0.0;
+  const double v1 = (bits & 2) ? fma(lo - (gv + sv), c.invd, -y1) : 0.0;
+  const double v2 = (bits & 4) ? fma(-sv, c.invd, -y2) : 0.0;
+  rr_s = fma(-c.ps[g], sv, (v1 - v0) + v2);
+  const double csg = (double)(((bits >> 1) & 1) - (bits & 1)) * c.invd;
+  return (v0 + v1) - csg * mss_pick(c, g, bits) * rr_s;
+}
+MPC_HD void dyn_rows6(const double* lin, double dt, const double* x, const double* xn, double* z) {
+  z[0] = xn[0] - (x[0] + lin[0] * x[2] + lin[1] * x[3]);
+  z[1] = xn[1] - (x[1] + lin[2] * x[2] + lin[3] * x[3]);
+  z[2] = xn[2] - (x[2] + lin[4] * x[5]);
+  z[3] = xn[3] - (x[3] + dt * x[4]);
+}
+
+MPC_HD void polish_rhs_fast(const View& w, const Params& p, const PolConst& c, int k) {
+  const int N = w.N;
+  double* rc = w.rec(k);
+  const bool reg = k < N;
+  const int act = w.act()[k];
+  double x[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) x[j] = rc[R_XU + j];
+  double out[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  double ua = 0.0, ud = 0.0;
+  if (k >= 1) {
+    const double* rp = w.rec(k - 1);
+    double xp[6], z[4];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) xp[j] = rp[R_XU + j];
+    ua = xp[4]; ud = xp[5];
+    dyn_rows6(rp + R_LIN, p.dt, xp, x, z);
+    const int ap = w.act()[k - 1];
+    const double b[4] = {rp[R_LIN + 5], rp[R_LIN + 6], 0.0, 0.0};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) out[r] = ((ap >> (15 + r)) & 1) ? fma(b[r] - z[r], c.invd, -rp[R_YE + r]) : 0.0;
+  } else {
+    const double* h = w.hdr();
+    const int ai = w.act()[N + 1];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) out[r] = ((ai >> r) & 1) ? fma(h[H_X0 + r] - x[r], c.invd, -h[H_YI + r]) : 0.0;
+  }
+  const double off0 = k == 0 ? c.up0 : 0.0, off1 = k == 0 ? c.up1 : 0.0;
+  const double gv[5] = {x[3], x[4], x[5], x[4] - (reg ? ua : 0.0), x[5] - (reg ? ud : 0.0)};
+  const double offs[5] = {0.0, 0.0, 0.0, off0, off1};
+  double G[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int g = 0; g < 5; ++g) {
+    if (g == 0 || reg) {
+      double rr_s;
+      G[g] = pol_group_val(c, g, (act >> (3 * g)) & 7, gv[g], rc[R_S + g], c.lo[g] + offs[g], c.hi[g] + offs[g],
+                           rc[R_V + 3 * g], rc[R_V + 3 * g + 1], rc[R_V + 3 * g + 2], rr_s);
+      rc[R_ST + g] = rr_s;
+    }
+  }
+  out[3] += G[0];
+  if (reg) {
+    const double* rn = w.rec(k + 1);
+    double xn[6], z[4];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) xn[j] = rn[R_XU + j];
+    const double* lin = rc + R_LIN;
+    dyn_rows6(lin, p.dt, x, xn, z);
+    const double b[4] = {lin[5], lin[6], 0.0, 0.0};
+    double d[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) d[r] = ((act >> (15 + r)) & 1) ? fma(b[r] - z[r], c.invd, -rc[R_YE + r]) : 0.0;
+    out[0] -= d[0];
+    out[1] -= d[1];
+    out[2] -= lin[0] * d[0] + lin[2] * d[1] + d[2];
+    out[3] -= lin[1] * d[0] + lin[3] * d[1] + d[3];
+    out[4] = G[1] + G[3] - p.dt * d[3];
+    out[5] = G[2] + G[4] - lin[4] * d[2];
+    if (k + 1 < N) {
+      const int an = w.act()[k + 1];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        double rr_s;
+        out[4 + i] -= pol_group_val(c, 3 + i, (an >> (3 * (3 + i))) & 7, xn[4 + i] - x[4 + i], rn[R_S + 3 + i], c.lo[3 + i], c.hi[3 + i],
+                                    rn[R_V + 3 * (3 + i)], rn[R_V + 3 * (3 + i) + 1], rn[R_V + 3 * (3 + i) + 2], rr_s);
+      }
+    }
+  }
+  const double* qd = reg ? p.q : p.qn;
+  int rev; double* bp = bx_ptr(w, k, rev);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double val = 0.0;
+    if (j < 4 || reg) {
+      const double pd = j < 4 ? 2.0 * qd[j < 4 ? j : 0] : 2.0 * p.r[j < 4 ? 0 : j - 4];
+      val = -(j < 4 ? rc[R_Q + j] : 0.0) - pd * x[j] + out[j];
+    }
+    bp[rev ? 5 - j : j] = val;
+  }
+  if (k == mid_stage(N)) {
+    double* bb = w.bottom().bx(N - k);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) bb[j] = 0.0;
+  }
+}
+
+MPC_HD void polish_dual_fast(const View& w, const Params& p, const PolConst& c, int k) {
+  const int N = w.N;
+  double* rc = w.rec(k);
+  const bool reg = k < N;
+  const int act = w.act()[k];
+  double x[6], dx[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) x[j] = rc[R_XU + j];
+  bx_load6(w, k, dx);
+  double ua = 0.0, ud = 0.0, dua_ = 0.0, dud_ = 0.0;
+  if (k >= 1 && reg) {
+    const double* rp = w.rec(k - 1);
+    ua = rp[R_XU + 4]; ud = rp[R_XU + 5];
+    double dp[6]; bx_load6(w, k - 1, dp); dua_ = dp[4]; dud_ = dp[5];
+  }
+  const double off0 = k == 0 ? c.up0 : 0.0, off1 = k == 0 ? c.up1 : 0.0;
+  const double offs[5] = {0.0, 0.0, 0.0, off0, off1};
+  const double gv[5] = {x[3], x[4], x[5], x[4] - ua, x[5] - ud};
+  const double gd[5] = {dx[3], dx[4], dx[5], dx[4] - dua_, dx[5] - dud_};
+#pragma unroll
+  for (int g = 0; g < 5; ++g) {
+    if (g == 0 || reg) {
+      const int bits = (act >> (3 * g)) & 7;
+      const double csg = (double)(((bits >> 1) & 1) - (bits & 1)) * c.invd;
+      const double ds = (rc[R_ST + g] - csg * gd[g]) * mss_pick(c, g, bits);
+      rc[R_ST + g] = ds;
+      const double sv = rc[R_S + g];
+      if (bits & 1) rc[R_V + 3 * g] += c.invd * ((gd[g] - ds) - ((c.hi[g] + offs[g]) - (gv[g] - sv)));
+      if (bits & 2) rc[R_V + 3 * g + 1] += c.invd * ((gd[g] + ds) - ((c.lo[g] + offs[g]) - (gv[g] + sv)));
+      if (bits & 4) rc[R_V + 3 * g + 2] += c.invd * (ds - (0.0 - sv));
+    }
+  }
+  if (reg) {
+    const double* rn = w.rec(k + 1);
+    double xn[6], dn[6], ax[4], ad[4];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) xn[j] = rn[R_XU + j];
+    bx_load6(w, k + 1, dn);
+    const double* lin = rc + R_LIN;
+    dyn_rows6(lin, p.dt, x, xn, ax);
+    dyn_rows6(lin, p.dt, dx, dn, ad);
+    const double b[4] = {lin[5], lin[6], 0.0, 0.0};
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if ((act >> (15 + r)) & 1) rc[R_YE + r] += c.invd * (ad[r] - (b[r] - ax[r]));
+  }
+  if (k == 0) {
+    double* h = w.hdr();
+    const int ai = w.act()[N + 1];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if ((ai >> r) & 1) h[H_YI + r] += c.invd * (dx[r] - (h[H_X0 + r] - x[r]));
+  }
+}
+
+// residual partial maxima (same seven entries as residual_stage); ymode 0: ADMM state, 1: polished pair
+MPC_HD void residual_fast(const View& w, const Params& p, const IterConst& c, int ymode, int k, double* r) {
+  const int N = w.N;
+  const double* rc = w.rec(k);
+  const bool reg = k < N;
+  double x[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) x[j] = rc[R_XU + j];
+  double aty[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  double ua = 0.0, ud = 0.0;
+  if (k >= 1) {
+    const double* rp = w.rec(k - 1);
+    ua = rp[R_XU + 4]; ud = rp[R_XU + 5];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) aty[q] = rp[R_YE + q];
+  } else {
+    const double* h = w.hdr();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      aty[q] = h[H_YI + q];
+      const double ax = x[q], b = h[H_X0 + q];
+      r[0] = dmax(r[0], fabs(ax - b)); r[1] = dmax(r[1], fabs(ax)); r[2] = dmax(r[2], fabs(b));
+    }
+  }
+  const double off0 = k == 0 ? c.up0 : 0.0, off1 = k == 0 ? c.up1 : 0.0;
+  const double offs[5] = {0.0, 0.0, 0.0, off0, off1};
+  const double gv[5] = {x[3], x[4], x[5], x[4] - (reg ? ua : 0.0), x[5] - (reg ? ud : 0.0)};
+  double Gy[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int g = 0; g < 5; ++g) {
+    if (g == 0 || reg) {
+      const double hi = c.hi[g] + offs[g], lo = c.lo[g] + offs[g];
+      const double sv = rc[R_S + g];
+      const double v0 = rc[R_V + 3 * g], v1 = rc[R_V + 3 * g + 1], v2 = rc[R_V + 3 * g + 2];
+      const double ax0 = gv[g] - sv, ax1 = gv[g] + sv, ax2 = sv;
+      double z0, z1, z2, y0, y1, y2;
+      if (ymode) { z0 = dmin2(ax0, hi); z1 = dmax2(ax1, lo); z2 = dmax2(ax2, 0.0); y0 = v0; y1 = v1; y2 = v2; }
+      else {
+        z0 = dmin2(v0, hi); z1 = dmax2(v1, lo); z2 = dmax2(v2, 0.0);
+        y0 = c.rho * (v0 - z0); y1 = c.rho * (v1 - z1); y2 = c.rho * (v2 - z2);
+      }
+      r[0] = dmax(r[0], dmax(fabs(ax0 - z0), dmax(fabs(ax1 - z1), fabs(ax2 - z2))));
+      r[1] = dmax(r[1], dmax(fabs(ax0), dmax(fabs(ax1), fabs(ax2))));
+      r[2] = dmax(r[2], dmax(fabs(z0), dmax(fabs(z1), fabs(z2))));
+      Gy[g] = y0 + y1;
+      const double px = c.ps_[g] * sv, ay = (y1 - y0) + y2;
+      r[3] = dmax(r[3], fabs(px + ay)); r[4] = dmax(r[4], fabs(px)); r[5] = dmax(r[5], fabs(ay));
+    }
+  }
+  aty[3] += Gy[0];
+  if (reg) {
+    const double* rn = w.rec(k + 1);
+    const double* lin = rc + R_LIN;
+    double xn[4], ax[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xn[j] = rn[R_XU + j];
+    ax[0] = xn[0] - (x[0] + lin[0] * x[2] + lin[1] * x[3]);
+    ax[1] = xn[1] - (x[1] + lin[2] * x[2] + lin[3] * x[3]);
+    ax[2] = xn[2] - (x[2] + lin[4] * x[5]);
+    ax[3] = xn[3] - (x[3] + p.dt * x[4]);
+    const double b[4] = {lin[5], lin[6], 0.0, 0.0};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      r[0] = dmax(r[0], fabs(ax[q] - b[q])); r[1] = dmax(r[1], fabs(ax[q])); r[2] = dmax(r[2], fabs(b[q]));
+    }
+    const double d0 = rc[R_YE + 0], d1 = rc[R_YE + 1], d2 = rc[R_YE + 2], d3 = rc[R_YE + 3];
+    aty[0] -= d0;
+    aty[1] -= d1;
+    aty[2] -= lin[0] * d0 + lin[2] * d1 + d2;
+    aty[3] -= lin[1] * d0 + lin[3] * d1 + d3;
+    aty[4] = Gy[1] + Gy[3] - p.dt * d3;
+    aty[5] = Gy[2] + Gy[4] - lin[4] * d2;
+    if (k + 1 < N) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const double v0 = rn[R_V + 3 * (3 + i)], v1 = rn[R_V + 3 * (3 + i) + 1];
+        double y0, y1;
+        if (ymode) { y0 = v0; y1 = v1; }
+        else { y0 = c.rho * (v0 - dmin2(v0, c.hi[3 + i])); y1 = c.rho * (v1 - dmax2(v1, c.lo[3 + i])); }
+        aty[4 + i] -= y0 + y1;
+      }
+    }
+  }
+  const double* qd = reg ? p.q : p.qn;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    if (j < 4 || reg) {
+      const double pd = j < 4 ? 2.0 * qd[j < 4 ? j : 0] : 2.0 * p.r[j < 4 ? 0 : j - 4];
+      const double px = pd * x[j], qj = j < 4 ? rc[R_Q + j] : 0.0;
+      r[3] = dmax(r[3], fabs(px + qj + aty[j])); r[4] = dmax(r[4], fabs(px)); r[5] = dmax(r[5], fabs(aty[j]));
+      r[6] = dmax(r[6], fabs(qj));
+    }
+  }
 }
 
 // save / restore the iterate of one stage to the HBM warm-start slot ([stage][30] + tail)

@@ -28,9 +28,9 @@ struct ProblemIO {
 struct Residuals { double pri, dua, eps_p, eps_d, sp, sd, nz, nq; };
 
 template <class Exec>
-MPC_HD Residuals compute_residuals(Exec& ex, const View& w, const Params& p, const Settings& s, double rho, int ymode) {
+MPC_HD Residuals compute_residuals(Exec& ex, const View& w, const Params& p, const Settings& s, const IterConst& ic, int ymode) {
   double r[7];
-  ex.reduce_max(w.N + 1, r, 7, [&](int k, double* rl) { residual_stage(w, p, rho, ymode, k, rl); });
+  ex.reduce_max(w.N + 1, r, 7, [&](int k, double* rl) { residual_fast(w, p, ic, ymode, k, rl); });
   Residuals o;
   o.pri = r[0]; o.dua = r[3];
   o.eps_p = s.eps_abs + s.eps_rel * dmax(r[1], r[2]);
@@ -105,6 +105,7 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
   // (n_pol > 0) or the restored ADMM iterate (n_pol == 0); pri/dua are updated accordingly.
   auto polish = [&](double pri0, double dua0) -> bool {
     const Mode pm = polish_mode(s);
+    const PolConst pc = pol_const(w, p, s);
     bool settled = false;
     int acc = 0, rejected = 0;
     double pp = pri0, dd = dua0;
@@ -119,12 +120,12 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
       ex.stages(NS, [&](int k) { assemble_stage(w, p, pm, k); });
       ex.factor(w); ++n_fac;
       for (int step = 0; step <= s.polish_refine_iter; ++step) {
-        ex.stages(NS, [&](int k) { polish_rhs_stage(w, p, pm, k); });
+        ex.stages(NS, [&](int k) { polish_rhs_fast(w, p, pc, k); });
         ex.solve(w); ++n_solve;
-        ex.stages(NS, [&](int k) { polish_dual_stage(w, p, pm, k); });
+        ex.stages(NS, [&](int k) { polish_dual_fast(w, p, pc, k); });
         ex.stages(NS, [&](int k) { polish_primal_stage(w, k); });
       }
-      Residuals rp = compute_residuals(ex, w, p, s, rho, 1);
+      Residuals rp = compute_residuals(ex, w, p, s, ic, 1);
       bool ok;
       if (pass == 0) {
         ok = (rp.pri < pp && rp.dua < dd) || (rp.pri < pp && dd < 1e-10) || (rp.dua < dd && pp < 1e-10);
@@ -161,7 +162,7 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
     const bool check = last || ((s.check_termination > 0) && (it % s.check_termination == 0));
     const bool adapt = !last && s.adaptive_rho && (s.adaptive_rho_interval > 0) && (it % s.adaptive_rho_interval == 0);
     if (check || adapt) {
-      ex.tag(3); res = compute_residuals(ex, w, p, se, rho, 0);
+      ex.tag(3); res = compute_residuals(ex, w, p, se, ic, 0);
       pri = res.pri; dua = res.dua;
       if (check) {
         const bool converged = res.pri <= res.eps_p && res.dua <= res.eps_d;

@@ -29,7 +29,7 @@ def pack(p, **s):
                     p.slack_velocity, p.slack_input, p.slack_rate], float)
     st = np.array([s.get("eps_abs", 1e-3), s.get("eps_rel", 1e-3), s.get("rho", 0.1), s.get("alpha", 1.6), s.get("sigma", 1e-6),
                    5.0, 1e3, 1e-6, 1e6, s.get("delta", 1e-6), s.get("max_iter", 60000), s.get("check_termination", 25),
-                   s.get("adaptive_rho", 1), s.get("adaptive_rho_interval", 50), s.get("polish_passes", 1), 3,
+                   s.get("adaptive_rho", 1), s.get("adaptive_rho_interval", 50), s.get("polish_passes", 1), s.get("polish_refine_iter", 3),
                    s.get("warm_start", 0), s.get("polish_retry", 0), s.get("early_polish", 0), s.get("early_polish_start", 50)], float)
     return par, st
 
