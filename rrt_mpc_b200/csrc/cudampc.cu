@@ -368,6 +368,7 @@ int cudampc_create(const cudampc_params* params, int max_batch, int device, cuda
     const int F = footprint(p.N);
     int P = (optin - (int)sizeof(CtaShared) - 64) / (F * (int)sizeof(double));
     if (P > 16) P = 16;
+    if (const char* pe = getenv("CUDAMPC_P")) { int v = atoi(pe); if (v >= 1 && v < P) P = v; }   // tuning knob
     h->cta_P = P;
     h->cta_smem = P * F * (int)sizeof(double) + (int)sizeof(CtaShared) + 16;
     h->cta_chunk = (half_bot(p.N) + 1) / 2;  // a (twisted) factorisation spreads over 2 rounds
