@@ -26,11 +26,7 @@ struct BatchArgs {
   int batch;
 };
 
-__device__ __forceinline__ int next_problem(int* counter, int lane) {
-  int p = 0;
-  if (lane == 0) p = atomicAdd(counter, 1);
-  return __shfl_sync(0xffffffffu, p, 0);
-}
+__device__ __forceinline__ int next_problem(int* counter, int lane) { return next_problem_warp(counter, lane); }
 
 // ------------------------------------------------------------------------------------------------
 // K_solve: batched MPCController.solve
@@ -60,8 +56,9 @@ __global__ void __launch_bounds__(32) mpc_solve_kernel(Params p, Settings s, Bat
   }
 }
 
-// MAXT = 256: up to 8 problems per CTA, 255 registers (software-pipelined sweeps); MAXT = 512: up to 16, 128 registers
-template <int MAXT>
+// MAXT x WPP variants: <384,2> two warps per problem (P <= 6; 170 registers), <256,1> P <= 8 (255 registers),
+// <512,1> P <= 16 (128 registers)
+template <int MAXT, int WPP>
 __global__ void __launch_bounds__(MAXT) mpc_solve_cta_kernel(Params p, Settings s, BatchArgs a, int P, int F, int chunk) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -70,10 +67,10 @@ __global__ void __launch_bounds__(MAXT) mpc_solve_cta_kernel(Params p, Settings 
   if (threadIdx.x == 0) sh->active = P;
   if (threadIdx.x < 32) sh->req[threadIdx.x] = 0;
   __syncthreads();
-  View w{smem + (size_t)warp * F, N};
-  CtaExec<false> ex{lane, warp, P, N, F, smem, sh, chunk};   // the hand-pipelined sweeps (PIPE) gain <10% and cost 190 registers
+  View w{smem + (size_t)(warp / WPP) * F, N};
+  CtaExec<WPP> ex{lane, warp, P, N, F, smem, sh, chunk};
   const int ws = warm_size(N);
-  for (int b = next_problem(a.counter, lane); b < a.batch; b = next_problem(a.counter, lane)) {
+  for (int b = ex.fetch(a.counter); b < a.batch; b = ex.fetch(a.counter)) {
     ProblemIO io;
     io.x0 = a.x0 + 4 * (size_t)b;
     io.ref = RefWin{a.ref + (size_t)4 * (N + 1) * b, 0, N + 1, 1.0};
@@ -87,7 +84,7 @@ __global__ void __launch_bounds__(MAXT) mpc_solve_cta_kernel(Params p, Settings 
     io.pri_res = a.pri ? a.pri + b : nullptr; io.dua_res = a.dua ? a.dua + b : nullptr;
     io.info = a.info ? a.info + 4 * (size_t)b : nullptr;
     solve_problem(ex, w, p, s, io);
-    __syncwarp();
+    ex.group_sync();
   }
   ex.drain();
 }
@@ -247,7 +244,7 @@ struct cudampc_handle {
   double *h_in, *h_out, *d_in, *d_out;
   size_t in_doubles, out_doubles;
   int sms, per_sm, smem_bytes;
-  int cta_P, cta_smem, cta_chunk, use_cta;
+  int cta_P, cta_smem, cta_chunk, use_cta, cta_wpp;
   long long launches;
   char err[512];
 };
@@ -375,8 +372,11 @@ int cudampc_create(const cudampc_params* params, int max_batch, int device, cuda
     const char* env = getenv("CUDAMPC_KERNEL");
     h->use_cta = (P >= 2) && !(env && strcmp(env, "warp") == 0);
     if (h->use_cta) {
-      e = (P <= 8) ? cudaFuncSetAttribute(mpc_solve_cta_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta_smem)
-                   : cudaFuncSetAttribute(mpc_solve_cta_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta_smem);
+      const char* we = getenv("CUDAMPC_WPP");
+      h->cta_wpp = (P <= 6 && p.N + 1 > 32 && !(we && atoi(we) == 1)) ? 2 : 1;   // two warps per problem pay off once a problem has more than 32 stages
+      e = h->cta_wpp == 2 ? cudaFuncSetAttribute(mpc_solve_cta_kernel<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta_smem)
+          : (P <= 8) ? cudaFuncSetAttribute(mpc_solve_cta_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta_smem)
+                     : cudaFuncSetAttribute(mpc_solve_cta_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta_smem);
       if (e != cudaSuccess) { delete h; return fail(nullptr, CUDAMPC_ERR_CUDA, "CUDA failure: %s", cudaGetErrorString(e)); }
       h->per_sm = P;
     }
@@ -488,8 +488,9 @@ int cudampc_solve_batch(cudampc_handle* h, int batch, const double* x0_dev, cons
   if (h->use_cta) {
     int grid = (batch + h->cta_P - 1) / h->cta_P;
     if (grid > h->sms) grid = h->sms;
-    if (h->cta_P <= 8) mpc_solve_cta_kernel<256><<<grid, 32 * h->cta_P, h->cta_smem, st>>>(h->p, s, a, h->cta_P, footprint(h->N), h->cta_chunk);
-    else mpc_solve_cta_kernel<512><<<grid, 32 * h->cta_P, h->cta_smem, st>>>(h->p, s, a, h->cta_P, footprint(h->N), h->cta_chunk);
+    if (h->cta_wpp == 2) mpc_solve_cta_kernel<384, 2><<<grid, 64 * h->cta_P, h->cta_smem, st>>>(h->p, s, a, h->cta_P, footprint(h->N), h->cta_chunk);
+    else if (h->cta_P <= 8) mpc_solve_cta_kernel<256, 1><<<grid, 32 * h->cta_P, h->cta_smem, st>>>(h->p, s, a, h->cta_P, footprint(h->N), h->cta_chunk);
+    else mpc_solve_cta_kernel<512, 1><<<grid, 32 * h->cta_P, h->cta_smem, st>>>(h->p, s, a, h->cta_P, footprint(h->N), h->cta_chunk);
   } else {
     int grid = h->sms * h->per_sm;
     if (grid > batch) grid = batch;

@@ -8,7 +8,7 @@
 using namespace mpc;
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
 
-struct TimedCta : CtaExec<false> {
+struct TimedCta : CtaExec<1> {
   long long acc[12]; int cur; long long t;   // 0..7 tags, 8 wait barrier A, 9 chain/idle between barriers, 10 wait B
   __device__ void tag(int g) { long long n = clock64(); acc[cur] += n - t; cur = g; t = n; }
   __device__ int round(int kind, const View& w, int i0, int i1) {
