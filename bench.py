@@ -38,6 +38,10 @@ EARLY_POLISH = 1          # finish as soon as a polish certifies a KKT point of 
 
 # canonical flop model of BASELINE.md §2 / SURVEY.md §8d (n = 11N+5, m = 19N+7, nnz(A) = 43N+5)
 _NNZ_L = {15: 706, 20: 941, 50: 2349}
+# DRAM traffic per solve of K_solve from the ncu --set full capture profiles/ncu_full_r01_solve_summary.txt
+# (dram__bytes_read.sum + dram__bytes_write.sum = 74.78 MB for a 4,096-problem launch): dominated by the
+# warm-start / polish back-up of the ADMM iterate (12 KB per save), not by the 4.1 KB of algorithmic I/O.
+TRAFFIC_BYTES_PER_SOLVE = 74.78e6 / 4096
 
 
 def flop_model(N: int):
@@ -324,7 +328,7 @@ def main():
                         "factorisations_mean": float(np.mean([m["n_fac_mean"] for m in allm])),
                         "problems_per_sm": ctl.problems_per_sm(), "smem_doubles_per_problem": ctl.workspace_doubles()},
         "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf > 0 else None,
-                     "traffic": None,
+                     "traffic": TRAFFIC_BYTES_PER_SOLVE * B, "traffic_unit": "bytes per launch (ncu r01, scaled per solve)",
                      "note": "binding roofline is the non-tensor fp64 pipe (SURVEY.md 8d); achieved = canonical flops (BASELINE.md model, from the "
                              "kernel's own iteration/factorisation counters) / CUDA-event time of one launch; peak = DFMA throughput measured "
                              "live by cudampc_fp64_peak_tflops (MEASURED_PEAKS.json has no fp64 figure)",
