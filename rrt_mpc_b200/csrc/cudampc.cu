@@ -364,7 +364,7 @@ int cudampc_create(const cudampc_params* params, int max_batch, int device, cuda
   {
     const int F = footprint(p.N);
     int P = (optin - (int)sizeof(CtaShared) - 64) / (F * (int)sizeof(double));
-    if (P > 16) P = 16;
+    if (P > 8) P = 8;          // 8 problems = 16 chain lanes; beyond that the 128-register budget of a 512-thread CTA spills (measured slower)
     if (const char* pe = getenv("CUDAMPC_P")) { int v = atoi(pe); if (v >= 1 && v < P) P = v; }   // tuning knob
     h->cta_P = P;
     h->cta_smem = P * F * (int)sizeof(double) + (int)sizeof(CtaShared) + 16;
@@ -501,6 +501,13 @@ int cudampc_solve_batch(cudampc_handle* h, int batch, const double* x0_dev, cons
   return CUDAMPC_OK;
 }
 
+static bool is_pinned(const void* p) {
+  if (!p) return true;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
 int cudampc_solve_batch_host(cudampc_handle* h, int batch, const double* x0, const double* ref, const double* u_prev,
                              const cudampc_settings* settings, double* u0, double* Xp, double* Up, int32_t* status,
                              int32_t* iters, double* pri_res, double* dua_res, int32_t* info, void* stream) {
@@ -513,21 +520,43 @@ int cudampc_solve_batch_host(cudampc_handle* h, int batch, const double* x0, con
   const int N = h->N;
   const size_t B = (size_t)batch;
   const size_t n_x0 = 4 * B, n_ref = 4 * (size_t)(N + 1) * B, n_up = 2 * B;
-  // inputs: pageable/pinned host -> pinned staging -> device (one copy)
-  memcpy(h->h_in, x0, n_x0 * sizeof(double));
-  memcpy(h->h_in + n_x0, ref, n_ref * sizeof(double));
-  if (u_prev) memcpy(h->h_in + n_x0 + n_ref, u_prev, n_up * sizeof(double));
-  else memset(h->h_in + n_x0 + n_ref, 0, n_up * sizeof(double));
-  const size_t n_in = n_x0 + n_ref + n_up;
-  CU(h, cudaMemcpyAsync(h->d_in, h->h_in, n_in * sizeof(double), cudaMemcpyHostToDevice, st));
-  // outputs, packed
   const size_t n_u0 = 2 * B, n_xp = 4 * (size_t)(N + 1) * B, n_upo = 2 * (size_t)N * B;
-  double* d_u0 = h->d_out; double* d_xp = d_u0 + n_u0; double* d_up = d_xp + n_xp;
-  double* d_pri = d_up + n_upo; double* d_dua = d_pri + B;
+  double* d_x0 = h->d_in; double* d_ref = d_x0 + n_x0; double* d_up = d_ref + n_ref;
+  double* d_u0 = h->d_out; double* d_xp = d_u0 + n_u0; double* d_upo = d_xp + n_xp;
+  double* d_pri = d_upo + n_upo; double* d_dua = d_pri + B;
   int32_t* d_int = reinterpret_cast<int32_t*>(d_dua + B);   // status[B], iters[B], info[4B]
-  int rc = cudampc_solve_batch(h, batch, h->d_in, h->d_in + n_x0, h->d_in + n_x0 + n_ref, settings, d_u0, d_xp, d_up,
-                               d_int, d_int + B, d_pri, d_dua, d_int + 2 * B, stream);
+  // page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are copied directly;
+  // pageable ones go through the handle's pinned staging area
+  const bool in_pinned = is_pinned(x0) && is_pinned(ref) && is_pinned(u_prev);
+  if (in_pinned) {
+    CU(h, cudaMemcpyAsync(d_x0, x0, n_x0 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(d_ref, ref, n_ref * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (u_prev) CU(h, cudaMemcpyAsync(d_up, u_prev, n_up * sizeof(double), cudaMemcpyHostToDevice, st));
+    else CU(h, cudaMemsetAsync(d_up, 0, n_up * sizeof(double), st));
+  } else {
+    memcpy(h->h_in, x0, n_x0 * sizeof(double));
+    memcpy(h->h_in + n_x0, ref, n_ref * sizeof(double));
+    if (u_prev) memcpy(h->h_in + n_x0 + n_ref, u_prev, n_up * sizeof(double));
+    else memset(h->h_in + n_x0 + n_ref, 0, n_up * sizeof(double));
+    CU(h, cudaMemcpyAsync(h->d_in, h->h_in, (n_x0 + n_ref + n_up) * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  int rc = cudampc_solve_batch(h, batch, d_x0, d_ref, d_up, settings, d_u0, d_xp, d_upo, d_int, d_int + B, d_pri, d_dua,
+                               d_int + 2 * B, stream);
   if (rc) return rc;
+  const bool out_pinned = is_pinned(u0) && is_pinned(Xp) && is_pinned(Up) && is_pinned(status) && is_pinned(iters) &&
+                          is_pinned(pri_res) && is_pinned(dua_res) && is_pinned(info);
+  if (out_pinned) {
+    CU(h, cudaMemcpyAsync(u0, d_u0, n_u0 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(Xp, d_xp, n_xp * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(Up, d_upo, n_upo * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (pri_res) CU(h, cudaMemcpyAsync(pri_res, d_pri, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (dua_res) CU(h, cudaMemcpyAsync(dua_res, d_dua, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(status, d_int, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(iters, d_int + B, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (info) CU(h, cudaMemcpyAsync(info, d_int + 2 * B, 4 * B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    return CUDAMPC_OK;
+  }
   const size_t n_out = n_u0 + n_xp + n_upo + 2 * B + 3 * B;   // 6 int32 per problem = 3 doubles
   CU(h, cudaMemcpyAsync(h->h_out, h->d_out, n_out * sizeof(double), cudaMemcpyDeviceToHost, st));
   CU(h, cudaStreamSynchronize(st));

@@ -214,8 +214,7 @@ class MPCController:
             up = np.ascontiguousarray(u_prev, dtype=np.float64)
             if up.shape != (B, 2):
                 raise ValueError(f"expected u_prev (B,2); got {up.shape}")
-        out = BatchResult(np.empty((B, 2)), np.empty((B, 4, N + 1)), np.empty((B, 2, N)), np.empty(B, np.int32),
-                          np.empty(B, np.int32), np.empty(B), np.empty(B), np.empty((B, 4), np.int32))
+        out = self._host_outputs(B, N)
         if B == 0:
             return out
         h = self._handle(B)
@@ -225,6 +224,20 @@ class MPCController:
                                             ptr(out.dua_res), ptr(out.info), None)
         _lib.check(h.lib, h.ptr, rc, "cudampc_solve_batch_host")
         return out
+
+    def _host_outputs(self, B: int, N: int) -> BatchResult:
+        """Result arrays of the host path.  With ``pinned_outputs`` they are views of page-locked torch tensors that are
+        reused from call to call (so the library copies straight into them, no staging) - copy what you keep."""
+        if not getattr(self, "pinned_outputs", False):
+            return BatchResult(np.empty((B, 2)), np.empty((B, 4, N + 1)), np.empty((B, 2, N)), np.empty(B, np.int32),
+                               np.empty(B, np.int32), np.empty(B), np.empty(B), np.empty((B, 4), np.int32))
+        import torch
+        cache = self.__dict__.setdefault("_pinned", {})
+        if cache.get("B") != B:
+            f = lambda *shape: torch.empty(shape, dtype=torch.float64).pin_memory()
+            i = lambda *shape: torch.empty(shape, dtype=torch.int32).pin_memory()
+            cache.update(B=B, t=(f(B, 2), f(B, 4, N + 1), f(B, 2, N), i(B), i(B), f(B), f(B), i(B, 4)))
+        return BatchResult(*(t.numpy() for t in cache["t"]))
 
     def _solve_batch_device(self, x0, ref, u_prev, s, stream) -> BatchResult:
         import torch
