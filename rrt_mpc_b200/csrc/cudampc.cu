@@ -142,78 +142,85 @@ __device__ __forceinline__ void f_discrete_dev(const Params& p, const double* x,
   out[3] = v + p.dt * u[0];
 }
 
-__global__ void __launch_bounds__(32) mpc_rollout_kernel(Params p, Settings s, cudampc_rollout_cfg cfg, RolloutArgs a) {
-  extern __shared__ double smem[];
-  const int lane = threadIdx.x & 31;
+// One vehicle, all steps (TrajectoryTracker.track loop body, control_stage.py:100-150), generic in the execution policy
+template <class Exec>
+__device__ __forceinline__ void rollout_vehicle(Exec& ex, const View& w, const Params& p, const Settings& s,
+                                                const cudampc_rollout_cfg& cfg, const RolloutArgs& a, int b) {
   const int N = p.N;
-  View w{smem, N};
-  WarpExec ex{lane};
   const int ws = warm_size(N);
   const int wk = 16 + 4 * (N + 1) + 2 * N;   // per-vehicle global scratch
   const double nan_ = __longlong_as_double(0x7ff8000000000000LL);
-  for (int b = next_problem(a.counter, lane); b < a.batch; b = next_problem(a.counter, lane)) {
-    double* wkb = a.work + (size_t)wk * b;   // [0..3] state, [4..5] u_prev, [6..7] u0, [8] pri, [9] dua, [10..13] info(int), 16.. Xp, Up
-    const double* refg = a.ref_global + (size_t)4 * a.ref_stride * b;
-    const int len = a.ref_len[b];
-    if (lane == 0) {
-      for (int i = 0; i < 4; ++i) wkb[i] = a.state0[4 * (size_t)b + i];
-      wkb[4] = 0.0; wkb[5] = 0.0;
+  double* wkb = a.work + (size_t)wk * b;     // [0..3] state, [4..5] u_prev, [6..7] u0, [10..11] status/iters (int), 16.. Xp, Up
+  const double* refg = a.ref_global + (size_t)4 * a.ref_stride * b;
+  const int len = a.ref_len[b];
+  ex.single([&]() {
+    for (int i = 0; i < 4; ++i) wkb[i] = a.state0[4 * (size_t)b + i];
+    wkb[4] = 0.0; wkb[5] = 0.0;
+  });
+  int path_idx = 0, flags = 0, nst = 0;
+  for (int step = 0; step < cfg.sim_steps; ++step) {
+    int* st_out = a.step_status ? a.step_status + (size_t)cfg.sim_steps * b + step : reinterpret_cast<int*>(wkb + 10);
+    int* it_out = a.step_iters ? a.step_iters + (size_t)cfg.sim_steps * b + step : reinterpret_cast<int*>(wkb + 10) + 1;
+    ProblemIO io;
+    io.x0 = wkb; io.u_prev = wkb + 4;
+    io.ref = RefWin{refg, path_idx, len, 1.0};
+    io.warm = a.warm + (size_t)ws * b; io.scratch = a.scratch + (size_t)ws * b;
+    io.u0 = wkb + 6; io.Xp = wkb + 16; io.Up = wkb + 16 + 4 * (N + 1);
+    io.status = st_out; io.iters = it_out; io.pri_res = nullptr; io.dua_res = nullptr; io.info = nullptr;
+    Settings ss = s;
+    ss.warm_start = (s.warm_start && step > 0) ? 1 : 0;
+    solve_problem(ex, w, p, ss, io);
+    ex.group_sync();
+    int status = *st_out;
+    if (status != STATUS_SOLVED && status != STATUS_SOLVED_INACCURATE && cfg.relax_on_failure) {
+      // control_stage.py:45-56: v_ref *= 0.6, du_bounds widened, one cold retry
+      Params pr = p;
+      pr.du_lo[0] -= cfg.relax_da; pr.du_hi[0] += cfg.relax_da;
+      pr.du_lo[1] -= cfg.relax_ddelta; pr.du_hi[1] += cfg.relax_ddelta;
+      io.ref.vscale = cfg.relax_v_scale;
+      ss.warm_start = 0;
+      solve_problem(ex, w, pr, ss, io);
+      ex.group_sync();
+      status = *st_out;
     }
-    __syncwarp();
-    int path_idx = 0, flags = 0, nst = 0;
-    for (int step = 0; step < cfg.sim_steps; ++step) {
-      int* st_out = a.step_status ? a.step_status + (size_t)cfg.sim_steps * b + step : reinterpret_cast<int*>(wkb + 10);
-      int* it_out = a.step_iters ? a.step_iters + (size_t)cfg.sim_steps * b + step : reinterpret_cast<int*>(wkb + 10) + 1;
-      ProblemIO io;
-      io.x0 = wkb; io.u_prev = wkb + 4;
-      io.ref = RefWin{refg, path_idx, len, 1.0};
-      io.warm = a.warm + (size_t)ws * b; io.scratch = a.scratch + (size_t)ws * b;
-      io.u0 = wkb + 6; io.Xp = wkb + 16; io.Up = wkb + 16 + 4 * (N + 1);
-      io.status = st_out; io.iters = it_out; io.pri_res = nullptr; io.dua_res = nullptr; io.info = nullptr;
-      Settings ss = s;
-      ss.warm_start = (s.warm_start && step > 0) ? 1 : 0;
-      solve_problem(ex, w, p, ss, io);
-      __syncwarp();
-      int status = *st_out;
-      if (status != STATUS_SOLVED && status != STATUS_SOLVED_INACCURATE && cfg.relax_on_failure) {
-        // control_stage.py:45-56: v_ref *= 0.6, du_bounds widened, one cold retry
-        Params pr = p;
-        pr.du_lo[0] -= cfg.relax_da; pr.du_hi[0] += cfg.relax_da;
-        pr.du_lo[1] -= cfg.relax_ddelta; pr.du_hi[1] += cfg.relax_ddelta;
-        io.ref.vscale = cfg.relax_v_scale;
-        ss.warm_start = 0;
-        solve_problem(ex, w, pr, ss, io);
-        __syncwarp();
-        status = *st_out;
-      }
-      if (status != STATUS_SOLVED && status != STATUS_SOLVED_INACCURATE) { flags |= 2; break; }
-      // integrate, carry u_prev, path index rule, goal test (control_stage.py:127-150)
-      double xn[4];
-      f_discrete_dev(p, wkb, wkb + 6, xn);
-      double u0a = wkb[6], u0d = wkb[7];
-      __syncwarp();
-      if (lane == 0) {
-        for (int i = 0; i < 4; ++i) { wkb[i] = xn[i]; a.states[((size_t)cfg.sim_steps * b + step) * 4 + i] = xn[i]; }
-        wkb[4] = u0a; wkb[5] = u0d;
-        if (a.controls) { a.controls[((size_t)cfg.sim_steps * b + step) * 2] = u0a; a.controls[((size_t)cfg.sim_steps * b + step) * 2 + 1] = u0d; }
-      }
-      __syncwarp();
-      nst = step + 1;
-      if (path_idx < len - 2) {
-        double dx = xn[0] - refg[4 * (size_t)path_idx], dy = xn[1] - refg[4 * (size_t)path_idx + 1];
-        if (dx * dx + dy * dy > cfg.advance_dist2) path_idx += 1;
-      }
-      if (hypot(xn[0] - a.goal[2 * (size_t)b], xn[1] - a.goal[2 * (size_t)b + 1]) < cfg.goal_radius) { flags |= 1; break; }
+    if (status != STATUS_SOLVED && status != STATUS_SOLVED_INACCURATE) { flags |= 2; break; }
+    // integrate, carry u_prev, path index rule, goal test (control_stage.py:127-150)
+    double xn[4];
+    f_discrete_dev(p, wkb, wkb + 6, xn);
+    const double u0a = wkb[6], u0d = wkb[7];
+    ex.group_sync();
+    ex.single([&]() {
+      for (int i = 0; i < 4; ++i) { wkb[i] = xn[i]; a.states[((size_t)cfg.sim_steps * b + step) * 4 + i] = xn[i]; }
+      wkb[4] = u0a; wkb[5] = u0d;
+      if (a.controls) { a.controls[((size_t)cfg.sim_steps * b + step) * 2] = u0a; a.controls[((size_t)cfg.sim_steps * b + step) * 2 + 1] = u0d; }
+    });
+    nst = step + 1;
+    if (path_idx < len - 2) {
+      double dx = xn[0] - refg[4 * (size_t)path_idx], dy = xn[1] - refg[4 * (size_t)path_idx + 1];
+      if (dx * dx + dy * dy > cfg.advance_dist2) path_idx += 1;
     }
-    // rows after the vehicle stopped
-    for (int i = nst * 4 + lane; i < cfg.sim_steps * 4; i += 32) a.states[(size_t)cfg.sim_steps * b * 4 + i] = nan_;
-    if (a.controls) for (int i = nst * 2 + lane; i < cfg.sim_steps * 2; i += 32) a.controls[(size_t)cfg.sim_steps * b * 2 + i] = nan_;
-    if (a.step_status) for (int i = nst + (flags & 2 ? 1 : 0) + lane; i < cfg.sim_steps; i += 32) a.step_status[(size_t)cfg.sim_steps * b + i] = 0;
-    if (a.step_iters) for (int i = nst + (flags & 2 ? 1 : 0) + lane; i < cfg.sim_steps; i += 32) a.step_iters[(size_t)cfg.sim_steps * b + i] = 0;
-    if (lane == 0) { a.n_steps[b] = nst; a.flags[b] = flags; }
-    __syncwarp();
+    if (hypot(xn[0] - a.goal[2 * (size_t)b], xn[1] - a.goal[2 * (size_t)b + 1]) < cfg.goal_radius) { flags |= 1; break; }
   }
+  // rows after the vehicle stopped
+  const int T = cfg.sim_steps, skip = nst + ((flags & 2) ? 1 : 0);
+  ex.stages(T * 4, [&](int i) { if (i >= nst * 4) a.states[(size_t)T * b * 4 + i] = nan_; });
+  if (a.controls) ex.stages(T * 2, [&](int i) { if (i >= nst * 2) a.controls[(size_t)T * b * 2 + i] = nan_; });
+  if (a.step_status) ex.stages(T, [&](int i) { if (i >= skip) a.step_status[(size_t)T * b + i] = 0; });
+  if (a.step_iters) ex.stages(T, [&](int i) { if (i >= skip) a.step_iters[(size_t)T * b + i] = 0; });
+  ex.single([&]() { a.n_steps[b] = nst; a.flags[b] = flags; });
 }
+
+__global__ void __launch_bounds__(32) mpc_rollout_kernel(Params p, Settings s, cudampc_rollout_cfg cfg, RolloutArgs a) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31;
+  View w{smem, p.N};
+  WarpExec ex{lane};
+  for (int b = next_problem(a.counter, lane); b < a.batch; b = next_problem(a.counter, lane)) rollout_vehicle(ex, w, p, s, cfg, a, b);
+}
+
+// (A CTA variant with the vehicles' sweeps in lock step, as in K_solve, measured SLOWER here - 427 k vs 702 k
+// vehicle-steps/s at N = 15: closed-loop steps are short warm-started solves dominated by setup and factorisation,
+// and the small footprint lets 15 independent warps share an SM.)
 
 // ------------------------------------------------------------------------------------------------
 // fp64 pipe peak (roofline denominator measured on the device the solver runs on)
@@ -244,7 +251,7 @@ struct cudampc_handle {
   double *h_in, *h_out, *d_in, *d_out;
   size_t in_doubles, out_doubles;
   int sms, per_sm, smem_bytes;
-  int cta_P, cta_smem, cta_chunk, use_cta, cta_wpp;
+  int cta_P, cta_smem, cta_chunk, use_cta, cta_wpp, warp_per_sm;
   long long launches;
   char err[512];
 };
@@ -360,6 +367,7 @@ int cudampc_create(const cudampc_params* params, int max_batch, int device, cuda
   if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mpc_solve_kernel, 32, h->smem_bytes);
   if (e != cudaSuccess || occ < 1) { delete h; return fail(nullptr, CUDAMPC_ERR_CUDA, "CUDA failure: %s", cudaGetErrorString(e)); }
   h->per_sm = occ;
+  h->warp_per_sm = occ;
   // transposed-chain kernel: one CTA per SM holding P problems (P <= 16: 512 threads x 128 registers)
   {
     const int F = footprint(p.N);
@@ -492,7 +500,7 @@ int cudampc_solve_batch(cudampc_handle* h, int batch, const double* x0_dev, cons
     else if (h->cta_P <= 8) mpc_solve_cta_kernel<256, 1><<<grid, 32 * h->cta_P, h->cta_smem, st>>>(h->p, s, a, h->cta_P, footprint(h->N), h->cta_chunk);
     else mpc_solve_cta_kernel<512, 1><<<grid, 32 * h->cta_P, h->cta_smem, st>>>(h->p, s, a, h->cta_P, footprint(h->N), h->cta_chunk);
   } else {
-    int grid = h->sms * h->per_sm;
+    int grid = h->sms * h->warp_per_sm;
     if (grid > batch) grid = batch;
     mpc_solve_kernel<<<grid, 32, h->smem_bytes, st>>>(h->p, s, a);
   }
@@ -597,9 +605,11 @@ int cudampc_rollout_batch(cudampc_handle* h, int batch, const double* ref_global
   a.warm = h->warm; a.scratch = h->scratch; a.work = h->work;
   a.states = states_dev; a.controls = controls_dev; a.n_steps = n_steps_dev; a.flags = flags_dev;
   a.step_status = step_status_dev; a.step_iters = step_iters_dev; a.counter = h->counter; a.batch = batch;
-  int grid = h->sms * h->per_sm;
-  if (grid > batch) grid = batch;
-  mpc_rollout_kernel<<<grid, 32, h->smem_bytes, st>>>(h->p, s, c, a);
+  {
+    int grid = h->sms * h->warp_per_sm;
+    if (grid > batch) grid = batch;
+    mpc_rollout_kernel<<<grid, 32, h->smem_bytes, st>>>(h->p, s, c, a);
+  }
   h->launches++;
   CU(h, cudaGetLastError());
   return CUDAMPC_OK;

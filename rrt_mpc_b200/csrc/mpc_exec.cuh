@@ -42,6 +42,7 @@ __device__ __forceinline__ void factor_twisted_lanes(int lane, const View& w, in
 struct WarpExec {
   int lane;
   __device__ __forceinline__ void tag(int) {}
+  __device__ __forceinline__ void group_sync() const { __syncwarp(); }
   template <class F> __device__ __forceinline__ void stages(int n, F f) {
     for (int k = lane; k < n; k += 32) f(k);
     __syncwarp();
