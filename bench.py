@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH, help="problems per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="problems in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--latency-launches", type=int, default=100, help="launches of one resident wave for the latency percentiles")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -271,6 +272,17 @@ def main():
     lit_flops = flops_of_batch(N, lit_iters, lit_info[:, 1], lit_info[:, 3])
     u0_gap = float((lres.u0 - res.u0).abs().max().item())
 
+    # ---- per-launch latency of one resident wave (BASELINE metric: p99 per-step latency) -----------------------------
+    wave = min(B, 148 * ctl.problems_per_sm())
+    lat = []
+    for i in range(args.latency_launches):
+        o = (i * wave) % max(1, B - wave + 1)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream); ctl.solve_batch(d_x0[o:o + wave], d_ref[o:o + wave], u_prev=d_up[o:o + wave]); a1.record(stream)
+        torch.cuda.synchronize(dev)
+        lat.append(a0.elapsed_time(a1))
+    lat = np.array(lat[5:]) if len(lat) > 10 else np.array(lat)
+
     # ---- end-to-end through the public API with host buffers ---------------------------------------
     ctl.pinned_outputs = True            # page-locked result arrays, reused per call (inputs are pinned above)
     for _ in range(1):
@@ -340,6 +352,8 @@ def main():
                          "frac": lit_flops / (lit_ms * 1e-3) / 1e12 / peak_tf if peak_tf > 0 else None, "max_abs_u0_gap_vs_early_polish": u0_gap,
                          "note": "same kernel with early_polish off: ADMM runs until the eps 1e-6 residual test passes, then polishes"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "latency": {"batch": int(wave), "launches": int(len(lat)), "p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
+                    "note": "one launch of exactly one resident wave of problems (SMs x problems/SM), device-resident, rank 0"},
         "gpu_launches": int(sum(m["launches"] for m in allm)),
         "clocks": clk,
         "cpu_baseline": cb,

@@ -9,6 +9,8 @@
  *                                (src/control/mpc_controller.py:39-141)
  *   cudampc_rollout_batch      <- TrajectoryTracker.track closed loop incl. _solve_with_relaxation
  *                                (src/pipeline/control_stage.py:33-56,74-157; vehicle_model.f_discrete :11-21)
+ *   cudampc_build_reference_batch <- build_reference(path, desired_speed, horizon, dt) -> (M,4) rows [x,y,yaw,v_ref]
+ *                                (src/control/ref_builder.py:10-22, src/common/geometry.py:9-45)
  *   cudampc_params            <- MPCParameters (src/control/mpc_controller.py:17-30; defaults src/config.py:66-92)
  *   cudampc_settings          <- the hard-coded OSQP settings (src/control/mpc_controller.py:121-131) + OSQP defaults
  *
@@ -137,6 +139,13 @@ int cudampc_solve_batch(cudampc_handle* h, int batch, const double* x0_dev, cons
 int cudampc_solve_batch_host(cudampc_handle* h, int batch, const double* x0, const double* ref, const double* u_prev,
                              const cudampc_settings* settings, double* u0, double* Xp, double* Up, int32_t* status,
                              int32_t* iters, double* pri_res, double* dua_res, int32_t* info, void* stream);
+
+/* build_reference for `batch` polylines (the input producer of the tracker).  Device pointers.
+ *   in : paths (B, max_pts, 2) with n_pts[b] valid points each; desired_speed = MPCConfig.v_px_s; dt and horizon from params
+ *   out: ref (B, ref_stride, 4) rows [x, y, unwrapped yaw, v_ref]; ref_len[b] = rows written, >= horizon+1 (tail padded);
+ *        a path that would need more than ref_stride rows is truncated to ref_stride (ref_len[b] == ref_stride). */
+int cudampc_build_reference_batch(cudampc_handle* h, int batch, const double* paths_dev, const int32_t* n_pts_dev, int max_pts,
+                                  double desired_speed, double* ref_dev, int32_t* ref_len_dev, int ref_stride, void* stream);
 
 /* Closed-loop tracking of `batch` vehicles for cfg->sim_steps steps without host round trips
  * (TrajectoryTracker.track semantics per vehicle: window gather with tail padding, solve (+relaxation),

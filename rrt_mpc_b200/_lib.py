@@ -36,7 +36,7 @@ class RolloutCfg(C.Structure):
 SYMBOLS = (
     "cudampc_version", "cudampc_default_settings", "cudampc_default_rollout_cfg", "cudampc_create",
     "cudampc_destroy", "cudampc_last_error", "cudampc_set_params", "cudampc_linearize_batch",
-    "cudampc_solve_batch", "cudampc_solve_batch_host", "cudampc_rollout_batch", "cudampc_workspace_doubles",
+    "cudampc_solve_batch", "cudampc_solve_batch_host", "cudampc_build_reference_batch", "cudampc_rollout_batch", "cudampc_workspace_doubles",
     "cudampc_problems_per_sm", "cudampc_launch_count", "cudampc_fp64_peak_tflops",
 )
 
@@ -73,6 +73,8 @@ def load() -> C.CDLL:
     lib.cudampc_solve_batch.restype = C.c_int
     lib.cudampc_solve_batch_host.argtypes = solve_args
     lib.cudampc_solve_batch_host.restype = C.c_int
+    lib.cudampc_build_reference_batch.argtypes = [vp, C.c_int, dp, ip, C.c_int, C.c_double, dp, ip, C.c_int, vp]
+    lib.cudampc_build_reference_batch.restype = C.c_int
     lib.cudampc_rollout_batch.argtypes = [vp, C.c_int, dp, ip, C.c_int, dp, dp, C.POINTER(Settings),
                                           C.POINTER(RolloutCfg), dp, dp, ip, ip, ip, ip, vp]
     lib.cudampc_rollout_batch.restype = C.c_int

@@ -135,35 +135,42 @@ class TrajectoryTracker:
     # -- batched, device-resident closed loop ---------------------------------------------------------
     def track_batch(self, paths: Sequence, starts, goals, *, map_resolution: float, sim_steps: Optional[int] = None,
                     ref_globals: Optional[Sequence[np.ndarray]] = None, states0=None, warm_start: bool = True,
-                    relax_on_failure: bool = True) -> BatchTrackingResult:
+                    relax_on_failure: bool = True, build_on_device: bool = True) -> BatchTrackingResult:
         """Track ``B`` vehicles. ``paths[b]`` is a polyline (as ``PlanResult.path``); ``starts``/``goals`` are
         ``(B,2)``.  Alternatively pass prebuilt ``ref_globals`` (each ``(M_b,4)``) and ``states0 (B,4)``."""
         import torch
         params = params_from_config(self.mpc, map_resolution)
         N = params.horizon
         T = int(self.mpc.sim_steps if sim_steps is None else sim_steps)
-        if ref_globals is None:
-            ref_globals = [build_reference(p, self.mpc.v_px_s, N, self.mpc.dt) for p in paths]
-        B = len(ref_globals)
+        dev = torch.device("cuda", self.device)
+        t = lambda a: torch.as_tensor(a).to(dev)
+        ctl = self._controller(params, key="rollout")
+        if ref_globals is None and build_on_device:
+            # the reference's build_reference (ref_builder.py:10-22) for all paths in one launch (K_ref)
+            B = len(paths)
+            d_ref, d_len = ctl.build_reference_batch(paths, float(self.mpc.v_px_s))
+            stride = int(d_ref.shape[1])
+        else:
+            if ref_globals is None:
+                ref_globals = [build_reference(p, self.mpc.v_px_s, N, self.mpc.dt) for p in paths]
+            B = len(ref_globals)
+            lens = np.array([len(r) for r in ref_globals], dtype=np.int32)
+            stride = int(lens.max())
+            refg = np.zeros((B, stride, 4))
+            for b, r in enumerate(ref_globals):
+                refg[b, :len(r)] = r
+            d_ref, d_len = t(refg), t(lens)
         if states0 is None:
             states0 = np.stack([initial_state(paths[b], starts[b]) for b in range(B)])
         states0 = np.ascontiguousarray(states0, dtype=np.float64).reshape(B, 4)
         goals = np.ascontiguousarray(goals, dtype=np.float64).reshape(B, 2)
-        lens = np.array([len(r) for r in ref_globals], dtype=np.int32)
-        stride = int(lens.max())
-        refg = np.zeros((B, stride, 4))
-        for b, r in enumerate(ref_globals):
-            refg[b, :len(r)] = r
-        dev = torch.device("cuda", self.device)
-        t = lambda a: torch.as_tensor(a).to(dev)
-        d_ref, d_len, d_s0, d_goal = t(refg), t(lens), t(states0), t(goals)
+        d_s0, d_goal = t(states0), t(goals)
         d_states = torch.empty((B, T, 4), dtype=torch.float64, device=dev)
         d_ctrl = torch.empty((B, T, 2), dtype=torch.float64, device=dev)
         d_n = torch.empty(B, dtype=torch.int32, device=dev)
         d_fl = torch.empty(B, dtype=torch.int32, device=dev)
         d_st = torch.empty((B, T), dtype=torch.int32, device=dev)
         d_it = torch.empty((B, T), dtype=torch.int32, device=dev)
-        ctl = self._controller(params, key="rollout")
         h = ctl._handle(B)
         s = replace(self.settings or SolverSettings(), warm_start=warm_start).to_c()
         cfg = _lib.RolloutCfg()

@@ -223,6 +223,78 @@ __global__ void __launch_bounds__(32) mpc_rollout_kernel(Params p, Settings s, c
 // and the small footprint lets 15 independent warps share an SM.)
 
 // ------------------------------------------------------------------------------------------------
+// K_ref: batched build_reference (src/control/ref_builder.py:10-22 + src/common/geometry.py:9-45), one thread per path:
+// arc-length resampling at step = max(2, 0.8 v dt) (np.arange + np.isclose end rule, np.interp two-pointer walk),
+// heading of successive differences with np.unwrap (first heading = atan2(0,0) = 0), curvature slow-down,
+// tail padding to horizon+1 rows.  Products/sums are written with explicit _rn intrinsics so that no fma contraction
+// changes the rounding of np.interp's  slope*(x - xp[j]) + fp[j].
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double interp_np(double x, double x0, double x1, double f0, double f1) {
+  if (x == x0) return f0;
+  const double slope = __ddiv_rn(__dsub_rn(f1, f0), __dsub_rn(x1, x0));
+  return __dadd_rn(__dmul_rn(slope, __dsub_rn(x, x0)), f0);
+}
+__global__ void mpc_build_reference_kernel(int batch, const double* paths, const int* n_pts, int max_pts, double v, double dt, int N,
+                                           double* ref, int* ref_len, int stride) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const double PI = 3.141592653589793;
+  const double* P = paths + (size_t)2 * max_pts * b;
+  double* R = ref + (size_t)4 * stride * b;
+  const int n = n_pts[b];
+  const double step = fmax(2.0, 0.8 * v * dt);
+  // total arc length (sequential cumsum, as np.cumsum)
+  double total = 0.0;
+  for (int i = 1; i < n; ++i) total = __dadd_rn(total, hypot(P[2 * i] - P[2 * i - 2], P[2 * i + 1] - P[2 * i - 1]));
+  int M = 0;
+  if (n < 2 || total < 1e-9) {
+    M = n < stride ? n : stride;
+    for (int i = 0; i < M; ++i) { R[4 * i] = P[2 * i]; R[4 * i + 1] = P[2 * i + 1]; }
+  } else {
+    int na = (int)ceil(total / step);                      // len(np.arange(0, total, step))
+    const double last = __dmul_rn((double)(na - 1), step);
+    const bool close = fabs(last - total) <= 1e-8 + 1e-5 * fabs(total);   // np.isclose(samples[-1], total)
+    M = close ? na : na + 1;
+    if (M > stride) M = stride;
+    int j = 0;                                             // current segment [s0, s1]
+    double s0 = 0.0, s1 = hypot(P[2] - P[0], P[3] - P[1]);
+    for (int i = 0; i < M; ++i) {
+      const double x = (i < na) ? __dmul_rn((double)i, step) : total;
+      while (j + 1 < n - 1 && x >= s1) {                   // np.interp: xp[j] <= x < xp[j+1]
+        ++j; s0 = s1;
+        s1 = __dadd_rn(s1, hypot(P[2 * j + 2] - P[2 * j], P[2 * j + 3] - P[2 * j + 1]));
+      }
+      if (x >= s1) { R[4 * i] = P[2 * (n - 1)]; R[4 * i + 1] = P[2 * (n - 1) + 1]; }       // x == xp[-1]
+      else { R[4 * i] = interp_np(x, s0, s1, P[2 * j], P[2 * j + 2]); R[4 * i + 1] = interp_np(x, s0, s1, P[2 * j + 1], P[2 * j + 3]); }
+    }
+  }
+  // heading (first difference is the zero vector), np.unwrap, slow-down
+  double prev_raw = 0.0, cum = 0.0, prev_un = 0.0;
+  for (int i = 0; i < M; ++i) {
+    const double dx = i ? R[4 * i] - R[4 * i - 4] : 0.0, dy = i ? R[4 * i + 1] - R[4 * i - 3] : 0.0;
+    const double raw = atan2(dy, dx);
+    if (i) {
+      const double dd = raw - prev_raw;
+      double ddmod = np_mod(dd + PI, 2.0 * PI) - PI;
+      if (ddmod == -PI && dd > 0.0) ddmod = PI;
+      double corr = ddmod - dd;
+      if (fabs(dd) < PI) corr = 0.0;
+      cum += corr;
+    }
+    const double un = raw + cum;
+    double hd = i ? fabs(un - prev_un) : 0.0;
+    hd = fmin(hd, PI - hd);
+    R[4 * i + 2] = un;
+    R[4 * i + 3] = v * (0.6 + 0.4 * (1.0 / (1.0 + 4.0 * hd)));
+    prev_raw = raw; prev_un = un;
+  }
+  int len = M;
+  for (; len < N + 1 && len < stride; ++len)
+    for (int c = 0; c < 4; ++c) R[4 * len + c] = R[4 * (M - 1) + c];
+  ref_len[b] = len;
+}
+
+// ------------------------------------------------------------------------------------------------
 // fp64 pipe peak (roofline denominator measured on the device the solver runs on)
 // ------------------------------------------------------------------------------------------------
 __global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {
@@ -578,6 +650,20 @@ int cudampc_solve_batch_host(cudampc_handle* h, int batch, const double* x0, con
   memcpy(status, hi, B * sizeof(int32_t));
   memcpy(iters, hi + B, B * sizeof(int32_t));
   if (info) memcpy(info, hi + 2 * B, 4 * B * sizeof(int32_t));
+  return CUDAMPC_OK;
+}
+
+int cudampc_build_reference_batch(cudampc_handle* h, int batch, const double* paths_dev, const int32_t* n_pts_dev, int max_pts,
+                                  double desired_speed, double* ref_dev, int32_t* ref_len_dev, int ref_stride, void* stream) {
+  if (!h) return CUDAMPC_ERR_INVALID;
+  if (batch < 0 || !paths_dev || !n_pts_dev || !ref_dev || !ref_len_dev || max_pts < 1 || ref_stride < h->N + 1 || !(desired_speed > 0.0))
+    return fail(h, CUDAMPC_ERR_INVALID, "%s", "build_reference_batch: NULL pointer, max_pts < 1, ref_stride < horizon+1 or speed <= 0");
+  if (batch == 0) return CUDAMPC_OK;
+  CU(h, cudaSetDevice(h->device));
+  mpc_build_reference_kernel<<<(batch + 63) / 64, 64, 0, (cudaStream_t)stream>>>(batch, paths_dev, n_pts_dev, max_pts, desired_speed, h->p.dt,
+                                                                                 h->N, ref_dev, ref_len_dev, ref_stride);
+  h->launches++;
+  CU(h, cudaGetLastError());
   return CUDAMPC_OK;
 }
 

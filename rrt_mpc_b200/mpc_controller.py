@@ -266,6 +266,34 @@ class MPCController:
         _lib.check(h.lib, h.ptr, rc, "cudampc_solve_batch")
         return out
 
+    def build_reference_batch(self, paths, desired_speed: float, *, stride: Optional[int] = None):
+        """``build_reference`` (ref_builder.py:10-22) for many polylines on the device.  ``paths``: sequence of ``(n_b, 2)``
+        arrays.  Returns ``(ref (B, stride, 4), ref_len (B,))`` as torch CUDA tensors (rows beyond ``ref_len[b]`` are
+        unspecified); feed them to ``cudampc_rollout_batch`` / ``TrajectoryTracker.track_batch``."""
+        import torch
+        N = self._params.horizon
+        B = len(paths)
+        npts = np.array([len(p) for p in paths], dtype=np.int32)
+        max_pts = int(npts.max()) if B else 1
+        buf = np.zeros((B, max_pts, 2))
+        for b, p in enumerate(paths):
+            buf[b, :len(p)] = np.asarray(p, dtype=float)
+        if stride is None:      # enough rows for the longest polyline: ceil(total / step) + 1, and at least N + 1
+            step = max(2.0, 0.8 * desired_speed * self._params.dt)
+            seg = np.hypot(*np.diff(buf, axis=1).transpose(2, 0, 1)) * (np.arange(1, max_pts)[None, :] < npts[:, None]) if max_pts > 1 else np.zeros((B, 1))
+            stride = int(max(N + 1, np.ceil(seg.sum(axis=1).max() / step) + 2, max_pts))
+        dev = torch.device("cuda", self._device)
+        d_paths, d_n = torch.as_tensor(buf).to(dev), torch.as_tensor(npts).to(dev)
+        ref = torch.empty((B, stride, 4), dtype=torch.float64, device=dev)
+        ref_len = torch.empty(B, dtype=torch.int32, device=dev)
+        h = self._handle(max(B, 1))
+        st = torch.cuda.current_stream(dev).cuda_stream
+        rc = h.lib.cudampc_build_reference_batch(h.ptr, B, C.c_void_p(d_paths.data_ptr()), C.c_void_p(d_n.data_ptr()), max_pts,
+                                                 C.c_double(desired_speed), C.c_void_p(ref.data_ptr()), C.c_void_p(ref_len.data_ptr()),
+                                                 stride, C.c_void_p(st))
+        _lib.check(h.lib, h.ptr, rc, "cudampc_build_reference_batch")
+        return ref, ref_len
+
     def linearize_batch(self, ref):
         """(A (B,N,4,4), B (B,N,4,2), c (B,N,4)) as ``solve`` linearises them (mpc_controller.py:59-70,108-109)."""
         import torch

@@ -183,3 +183,29 @@ def test_invalid_arguments_fail_loudly():
     q = np.diag([4.0, 4.0, 0.6, 0.1]); q[0, 1] = q[1, 0] = 0.1
     with pytest.raises(RuntimeError, match="non-diagonal"):
         MPCController(dataclasses.replace(product_params(20), q=q)).solve(np.zeros(4), np.zeros((21, 4)))
+
+
+def test_build_reference_batch_matches_reference_producer():
+    """K_ref against build_reference outputs of the REAL reference (tests/golden/ref_builder.npz, default scenario)."""
+    g = load_golden("ref_builder.npz")
+    d = load_golden("default_scenario.npz")
+    by_cfg = {}
+    for i in range(12):
+        v, N, dt = g[f"args{i}"]
+        by_cfg.setdefault((float(v), int(N), float(dt)), []).append(i)
+    from rrt_mpc_b200 import MPCConfig, MPCController
+    for (v, N, dt), idx in by_cfg.items():
+        ctl = MPCController(MPCConfig(horizon=N, dt=dt).to_parameters(0.8))
+        ref, ref_len = ctl.build_reference_batch([g[f"path{i}"] for i in idx], v)
+        ref, ref_len = ref.cpu().numpy(), ref_len.cpu().numpy()
+        for k, i in enumerate(idx):
+            want = g[f"ref{i}"]
+            assert ref_len[k] == len(want), (i, ref_len[k], len(want))
+            got = ref[k, :len(want)]
+            assert np.abs(got[:, :2] - want[:, :2]).max() <= 1e-12 * np.abs(want[:, :2]).max()
+            assert np.abs(got[:, 2] - want[:, 2]).max() <= 1e-12 * max(1.0, np.abs(want[:, 2]).max())
+            assert np.abs(got[:, 3] - want[:, 3]).max() <= 1e-12 * v
+    ctl = MPCController(MPCConfig().to_parameters(0.8))
+    ref, ref_len = ctl.build_reference_batch([d["path"]] * 3, 15.0)
+    assert int(ref_len[0]) == 45
+    assert np.abs(ref[1, :45].cpu().numpy() - d["ref_global"]).max() <= 1e-12 * 100
