@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(32) mpc_solve_kernel(Params p, Settings s, Bat
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;
   const int N = p.N;
-  View w{smem, N};
+  View w{smem, N, 0, 0};
   WarpExec ex{lane};
   const int ws = warm_size(N);
   for (int b = next_problem(a.counter, lane); b < a.batch; b = next_problem(a.counter, lane)) {
@@ -67,8 +67,9 @@ __global__ void __launch_bounds__(MAXT) mpc_solve_cta_kernel(Params p, Settings 
   if (threadIdx.x == 0) sh->active = P;
   if (threadIdx.x < 32) sh->req[threadIdx.x] = 0;
   __syncthreads();
-  View w{smem + (size_t)(warp / WPP) * F, N};
-  CtaExec<WPP> ex{lane, warp, P, N, F, smem, sh, chunk};
+  int fpad, xpad; layout_pads(N, P, fpad, xpad);
+  View w{smem + (size_t)(warp / WPP) * F, N, fpad, xpad};
+  CtaExec<WPP> ex{lane, warp, P, N, F, smem, sh, chunk, fpad, xpad};
   const int ws = warm_size(N);
   for (int b = ex.fetch(a.counter); b < a.batch; b = ex.fetch(a.counter)) {
     ProblemIO io;
@@ -213,7 +214,7 @@ __device__ __forceinline__ void rollout_vehicle(Exec& ex, const View& w, const P
 __global__ void __launch_bounds__(32) mpc_rollout_kernel(Params p, Settings s, cudampc_rollout_cfg cfg, RolloutArgs a) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;
-  View w{smem, p.N};
+  View w{smem, p.N, 0, 0};
   WarpExec ex{lane};
   for (int b = next_problem(a.counter, lane); b < a.batch; b = next_problem(a.counter, lane)) rollout_vehicle(ex, w, p, s, cfg, a, b);
 }

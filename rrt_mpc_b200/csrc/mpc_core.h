@@ -94,15 +94,27 @@ enum { BLK = 44 };
 MPC_HD int mid_stage(int N) { return N / 2; }
 MPC_HD int half_top(int N) { return mid_stage(N) + 1; }          // local stages of the top half (last = middle = border)
 MPC_HD int half_bot(int N) { return N - mid_stage(N) + 1; }      // local stages of the bottom half (last = middle = border)
-MPC_HD int bx_doubles(int N) { return 7 * (half_top(N) + 2) + 7 * (half_bot(N) + 2); }
+MPC_HD int bx_doubles(int N) { return 7 * (half_top(N) + 2) + 7 * (half_bot(N) + 2) + 1; }
 MPC_HD int band_offset(int N) {           // even => 16-byte aligned blocks
   int o = hdr_size(N) + (N + 1) * SR + bx_doubles(N);
   return (o + 1) & ~1;
 }
+enum { PAD_MAX = 16 };                     // room for the bank-conflict pads of the bottom half (fpad, xpad)
 MPC_HD int footprint(int N) {
-  int f = band_offset(N) + BLK * (half_top(N) + 1) + BLK * (half_bot(N) + 1) + 22;
+  int f = band_offset(N) + BLK * (half_top(N) + 1) + BLK * (half_bot(N) + 1) + 22 + PAD_MAX + 2;
   while ((f & 3) != 2) ++f;               // F = 2 (mod 4): conflict-free 128-bit loads when lanes stride over problems
   return f;
+}
+// Pads that make the chain warp's accesses conflict-free when lanes 0..P-1 read top halves and lanes P..2P-1 bottom
+// halves of P problems F doubles apart: the bottom half's factor blocks are shifted by P 16-byte columns (mod 8)
+// relative to the top half's, its rhs/solution rows by an odd number of 8-byte bank pairs.
+MPC_HD void layout_pads(int N, int P, int& fpad, int& xpad) {
+  const int F = footprint(N);
+  const int q = (F / 2) & 7;                                   // 16-byte columns per problem (odd)
+  const int nat = ((BLK * (half_top(N) + 1)) / 2) & 7;         // natural column offset of the bottom half
+  const int want = (P * q) & 7;
+  fpad = 2 * ((want - nat) & 7);
+  xpad = ((7 * (half_top(N) + 2)) & 1) ? 0 : 1;                // make the bottom rows' offset odd
 }
 // warm-start state kept in HBM between calls: per stage xu(6) s(5) v(15) ye(4), + yi(4) + rho
 MPC_HD int warm_size(int N) { return 30 * (N + 1) + 5; }
@@ -117,6 +129,7 @@ struct HalfView {
 struct View {
   double* base;
   int N;
+  int fpad, xpad;    // bank-conflict pads of the bottom half (layout_pads)
   MPC_HD double* hdr() const { return base; }
   MPC_HD int* act() const { return reinterpret_cast<int*>(base + H_ACT); }  // [N+1] stage masks + [N+1]=init rows
   MPC_HD double* rec(int k) const { return base + hdr_size(N) + k * SR; }
@@ -124,9 +137,9 @@ struct View {
   MPC_HD double* scratch() const { return bx_base(); }                       // >= N+1 doubles, free before the first solve
   MPC_HD HalfView top() const { return HalfView{bx_base() + 7, base + band_offset(N), half_top(N)}; }
   MPC_HD HalfView bottom() const {
-    return HalfView{bx_base() + 7 * (half_top(N) + 2) + 7, base + band_offset(N) + BLK * (half_top(N) + 1), half_bot(N)};
+    return HalfView{bx_base() + 7 * (half_top(N) + 2) + 7 + xpad, base + band_offset(N) + BLK * (half_top(N) + 1) + fpad, half_bot(N)};
   }
-  MPC_HD double* mid() const { return base + band_offset(N) + BLK * (half_top(N) + 1) + BLK * (half_bot(N) + 1); }
+  MPC_HD double* mid() const { return base + band_offset(N) + BLK * (half_top(N) + 1) + BLK * (half_bot(N) + 1) + PAD_MAX; }
   // element (k, j) of the right-hand side / solution vector in the twisted storage
   MPC_HD double bx_get(int k, int j) const {
     const int m = mid_stage(N);

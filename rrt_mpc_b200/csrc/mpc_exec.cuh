@@ -114,6 +114,7 @@ struct CtaExec {
   double* smem0;
   CtaShared* sh;
   int chunk;       // factor stages per round
+  int fpad, xpad;  // bank-conflict pads of every problem's layout in this CTA
   __device__ __forceinline__ int prob() const { return warp / WPP; }
   __device__ __forceinline__ int gl() const { return (warp % WPP) * 32 + lane; }      // lane within the group
   __device__ __forceinline__ void group_sync() const {
@@ -175,7 +176,7 @@ struct CtaExec {
       // lanes 0..P-1: top halves, lanes P..2P-1: bottom halves of the P problems of this CTA
       const int pr = lane < P ? lane : (lane < 2 * P ? lane - P : 0);
       const bool act = lane < 2 * P && sh->req[pr];
-      View v{smem0 + (size_t)pr * F, N};
+      View v{smem0 + (size_t)pr * F, N, fpad, xpad};
       chain_twisted_lanes<false>(act, lane >= P, lane < P ? lane + P : (lane < 2 * P ? lane - P : lane), v);
     }
     if (kind == 2 && warp % WPP == 0) factor_twisted_lanes(lane, w, i0, i1, i1 >= hmax());
@@ -190,7 +191,7 @@ struct CtaExec {
   }
   __device__ __forceinline__ void drain() {
     if (gl() == 0) atomicSub(&sh->active, 1);
-    while (round(0, View{smem0, N}, 0, 0) > 0) {}
+    while (round(0, View{smem0, N, fpad, xpad}, 0, 0) > 0) {}
   }
 };
 

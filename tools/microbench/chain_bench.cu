@@ -20,7 +20,8 @@ __global__ void bench(int N, int F, int P, int reps, long long* cyc, double* sin
   __syncthreads();
   if (threadIdx.x < 32) {
     const int prob = lane < P ? lane : (lane < 2 * P ? lane - P : 0);
-    View w{smem + (size_t)prob * F, N};
+    int fpad, xpad; layout_pads(N, P, fpad, xpad);
+    View w{smem + (size_t)prob * F, N, fpad, xpad};
     if (lane < P) { fill(w); factor_band(w); }
     __syncwarp();
     const bool act = lane < 2 * P;

@@ -9,7 +9,7 @@ __global__ void parts(int N, int reps, long long* cyc, double* sink) {
   extern __shared__ double smem[];
   for (int i = threadIdx.x; i < footprint(N); i += blockDim.x) smem[i] = 0.001 * ((i * 37) % 11);
   __syncthreads();
-  View w{smem, N};
+  View w{smem, N, 0, 0};
   double a[6] = {1, 2, 3, 4, 5, 6}, out[6];
   ChainRegs r;
   chain_load_fwd(w, 0, r);

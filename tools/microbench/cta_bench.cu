@@ -21,7 +21,7 @@ struct TimedCta : CtaExec<1> {
     if (warp == 0) {
       const int prob = lane < P ? lane : lane - P;
       const bool act = lane < 2 * P && sh->req[prob < P ? prob : 0];
-      View v{smem0 + (size_t)(prob < P ? prob : 0) * F, N};
+      View v{smem0 + (size_t)(prob < P ? prob : 0) * F, N, fpad, xpad};
       chain_twisted_lanes<false>(act, lane >= P, lane < P ? lane + P : (lane < 2 * P ? lane - P : lane), v);
     }
     tag(11);
@@ -33,7 +33,7 @@ struct TimedCta : CtaExec<1> {
   }
   __device__ void solve(const View& w) { round(1, w, 0, 0); }
   __device__ void factor(const View& w) { const int n = hmax(); for (int i0 = 0; i0 < n; i0 += chunk) round(2, w, i0, min(i0 + chunk, n)); }
-  __device__ void drain() { if (lane == 0) atomicSub(&sh->active, 1); while (round(0, View{smem0, N}, 0, 0) > 0) {} }
+  __device__ void drain() { if (lane == 0) atomicSub(&sh->active, 1); while (round(0, View{smem0, N, fpad, xpad}, 0, 0) > 0) {} }
 };
 
 __global__ void __launch_bounds__(256) k(Params p, Settings s, int P, int F, const double* x0, const double* ref, const double* up, double* warm, double* out, long long* cyc, int* iters) {
@@ -43,8 +43,9 @@ __global__ void __launch_bounds__(256) k(Params p, Settings s, int P, int F, con
   if (threadIdx.x == 0) sh->active = P;
   if (threadIdx.x < 32) sh->req[threadIdx.x] = 0;
   __syncthreads();
-  View w{smem + (size_t)warp * F, N};
-  TimedCta ex; ex.lane = lane; ex.warp = warp; ex.P = P; ex.N = N; ex.F = F; ex.smem0 = smem; ex.sh = sh; ex.chunk = (half_bot(N) + 1) / 2;
+  int fpad_, xpad_; layout_pads(N, P, fpad_, xpad_);
+  View w{smem + (size_t)warp * F, N, fpad_, xpad_};
+  TimedCta ex; ex.lane = lane; ex.warp = warp; ex.P = P; ex.N = N; ex.F = F; ex.smem0 = smem; ex.sh = sh; ex.chunk = (half_bot(N) + 1) / 2; ex.fpad = fpad_; ex.xpad = xpad_;
   for (int i = 0; i < 12; ++i) ex.acc[i] = 0; ex.cur = 0; ex.t = clock64();
   ProblemIO io; io.x0 = x0 + 4 * warp; io.ref = RefWin{ref + 4 * (N + 1) * warp, 0, N + 1, 1.0}; io.u_prev = up + 2 * warp;
   io.warm = warm + 2 * warm_size(N) * warp; io.scratch = io.warm + warm_size(N);

@@ -23,7 +23,7 @@ struct TimedExec {
 };
 __global__ void k(Params p, Settings s, const double* x0, const double* ref, const double* up, double* warm, double* out, long long* cyc, int* cnt, int* iters) {
   extern __shared__ double smem[];
-  View w{smem, p.N};
+  View w{smem, p.N, 0, 0};
   TimedExec ex; ex.lane = threadIdx.x; for (int i = 0; i < 8; ++i) { ex.acc[i] = 0; ex.cnt[i] = 0; } ex.cur = 0; ex.t = clock64();
   ProblemIO io; io.x0 = x0; io.ref = RefWin{ref, 0, p.N + 1, 1.0}; io.u_prev = up; io.warm = warm; io.scratch = warm + warm_size(p.N);
   io.u0 = out; io.Xp = out + 2; io.Up = out + 2 + 4 * (p.N + 1); int st, info[4]; double pr, du;
