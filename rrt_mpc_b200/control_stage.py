@@ -49,6 +49,16 @@ class BatchTrackingResult:
     def result(self, b: int) -> TrackingResult:
         return TrackingResult(states=[self.states[b, t].copy() for t in range(int(self.n_steps[b]))])
 
+    def save_npz(self, path: str) -> None:
+        """Telemetry export (the reference keeps only the post-step states, artifacts.py:34-38): every array of the roll-out."""
+        np.savez_compressed(path, states=self.states, controls=self.controls, n_steps=self.n_steps, goal_reached=self.goal_reached,
+                            aborted=self.aborted, step_status=self.step_status, step_iters=self.step_iters)
+
+    @staticmethod
+    def load_npz(path: str) -> "BatchTrackingResult":
+        d = np.load(path)
+        return BatchTrackingResult(**{k: d[k] for k in ("states", "controls", "n_steps", "goal_reached", "aborted", "step_status", "step_iters")})
+
 
 def initial_state(path, start) -> np.ndarray:
     """control_stage.py:79-84: heading of the first path segment, v0 = 5.0."""

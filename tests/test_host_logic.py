@@ -67,3 +67,17 @@ def test_initial_state_matches_reference_rule():
     assert s[0] == 70.0 and s[1] == 70.0 and s[3] == 5.0
     assert s[2] == pytest.approx(np.arctan2(d["path"][1, 1] - d["path"][0, 1], d["path"][1, 0] - d["path"][0, 0]))
     assert initial_state([(1.0, 2.0)], (1.0, 2.0))[2] == 0.0
+
+
+def test_batch_tracking_result_roundtrip(tmp_path):
+    from rrt_mpc_b200 import BatchTrackingResult
+    T = 5
+    states = np.full((2, T, 4), np.nan); states[0, :3] = np.arange(12).reshape(3, 4); states[1, :5] = 1.0
+    r = BatchTrackingResult(states=states, controls=np.zeros((2, T, 2)), n_steps=np.array([3, 5], np.int32), goal_reached=np.array([True, False]),
+                            aborted=np.array([False, False]), step_status=np.ones((2, T), np.int32), step_iters=np.full((2, T), 25, np.int32))
+    f = str(tmp_path / "roll.npz")
+    r.save_npz(f)
+    q = BatchTrackingResult.load_npz(f)
+    assert np.array_equal(q.n_steps, r.n_steps) and np.array_equal(np.isnan(q.states), np.isnan(r.states))
+    tr = q.result(0)                                       # what TrackingResult.states holds for vehicle 0 (artifacts.py:34-38)
+    assert len(tr.states) == 3 and np.array_equal(tr.states[2], [8.0, 9.0, 10.0, 11.0])
