@@ -1,10 +1,11 @@
 // cudampc.cu — libcudampc.so: CUDA kernels (sm_100a) + C ABI (include/cudampc.h).
 //
-// One warp owns one tracking problem; the whole problem (ADMM iterate, linearisation, banded LDL' factor,
-// right-hand side) lives in shared memory for the entire solve (DESIGN.md §data layout).  Stage-parallel
-// phases run with lanes striding over the N+1 stages; the banded factorisation / triangular sweeps are
-// the sequential chain.  Warps fetch problems from a global counter, so a launch is persistent:
-// grid = SMs x resident-problems-per-SM regardless of the batch size.
+// A group of warps (one warp up to horizon ~80, two beyond) owns one tracking problem; the whole problem (ADMM
+// iterate, linearisation, banded LDL' factor, right-hand side) lives in shared memory for the entire solve
+// (DESIGN.md §3).  Stage-parallel phases run with lanes striding over the N+1 stages; the banded factorisation /
+// triangular sweeps are the sequential chain (twisted: two lanes, one per half of the horizon).  One CTA per SM
+// holds as many groups as shared memory allows; groups are independent of each other and fetch problems from a
+// global counter, so a launch is persistent: grid = SMs regardless of the batch size.
 //
 // There is no CPU fallback: every entry point fails with CUDAMPC_ERR_CUDA if the device is unusable.
 #include <cuda_runtime.h>
@@ -26,50 +27,19 @@ struct BatchArgs {
   int batch;
 };
 
-__device__ __forceinline__ int next_problem(int* counter, int lane) { return next_problem_warp(counter, lane); }
-
 // ------------------------------------------------------------------------------------------------
-// K_solve: batched MPCController.solve
+// K_solve: batched MPCController.solve.  The CTA holds P problems, each owned by a group of WPP warps (GroupExec).
+// <256,1>: P <= 8 one-warp groups, 255 registers; <128,2>: P <= 2 two-warp groups for long horizons.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) mpc_solve_kernel(Params p, Settings s, BatchArgs a) {
-  extern __shared__ double smem[];
-  const int lane = threadIdx.x & 31;
-  const int N = p.N;
-  View w{smem, N, 0, 0};
-  WarpExec ex{lane};
-  const int ws = warm_size(N);
-  for (int b = next_problem(a.counter, lane); b < a.batch; b = next_problem(a.counter, lane)) {
-    ProblemIO io;
-    io.x0 = a.x0 + 4 * (size_t)b;
-    io.ref = RefWin{a.ref + (size_t)4 * (N + 1) * b, 0, N + 1, 1.0};
-    io.u_prev = a.u_prev ? a.u_prev + 2 * (size_t)b : nullptr;
-    io.warm = a.warm + (size_t)ws * b;
-    io.scratch = a.scratch + (size_t)ws * b;
-    io.u0 = a.u0 + 2 * (size_t)b;
-    io.Xp = a.Xp + (size_t)4 * (N + 1) * b;
-    io.Up = a.Up + (size_t)2 * N * b;
-    io.status = a.status + b; io.iters = a.iters + b;
-    io.pri_res = a.pri ? a.pri + b : nullptr; io.dua_res = a.dua ? a.dua + b : nullptr;
-    io.info = a.info ? a.info + 4 * (size_t)b : nullptr;
-    solve_problem(ex, w, p, s, io);
-    __syncwarp();
-  }
-}
-
-// MAXT x WPP variants: <384,2> two warps per problem (P <= 6; 170 registers), <256,1> P <= 8 (255 registers),
-// <512,1> P <= 16 (128 registers)
 template <int MAXT, int WPP>
-__global__ void __launch_bounds__(MAXT) mpc_solve_cta_kernel(Params p, Settings s, BatchArgs a, int P, int F, int chunk) {
+__global__ void __launch_bounds__(MAXT) mpc_solve_kernel(Params p, Settings s, BatchArgs a, int P, int F) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int N = p.N;
-  CtaShared* sh = reinterpret_cast<CtaShared*>(smem + (size_t)P * F);
-  if (threadIdx.x == 0) sh->active = P;
-  if (threadIdx.x < 32) sh->req[threadIdx.x] = 0;
-  __syncthreads();
-  int fpad, xpad; layout_pads(N, P, fpad, xpad);
+  GroupShared* sh = reinterpret_cast<GroupShared*>(smem + (size_t)P * F) + warp / WPP;
+  int fpad, xpad; layout_pads(N, fpad, xpad);
   View w{smem + (size_t)(warp / WPP) * F, N, fpad, xpad};
-  CtaExec<WPP> ex{lane, warp, P, N, F, smem, sh, chunk, fpad, xpad};
+  GroupExec<WPP> ex{lane, warp, sh};
   const int ws = warm_size(N);
   for (int b = ex.fetch(a.counter); b < a.batch; b = ex.fetch(a.counter)) {
     ProblemIO io;
@@ -87,7 +57,6 @@ __global__ void __launch_bounds__(MAXT) mpc_solve_cta_kernel(Params p, Settings 
     solve_problem(ex, w, p, s, io);
     ex.group_sync();
   }
-  ex.drain();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -214,14 +183,11 @@ __device__ __forceinline__ void rollout_vehicle(Exec& ex, const View& w, const P
 __global__ void __launch_bounds__(32) mpc_rollout_kernel(Params p, Settings s, cudampc_rollout_cfg cfg, RolloutArgs a) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;
-  View w{smem, p.N, 0, 0};
-  WarpExec ex{lane};
-  for (int b = next_problem(a.counter, lane); b < a.batch; b = next_problem(a.counter, lane)) rollout_vehicle(ex, w, p, s, cfg, a, b);
+  int fpad, xpad; layout_pads(p.N, fpad, xpad);
+  View w{smem, p.N, fpad, xpad};
+  GroupExec<1> ex{lane, 0, nullptr};
+  for (int b = ex.fetch(a.counter); b < a.batch; b = ex.fetch(a.counter)) rollout_vehicle(ex, w, p, s, cfg, a, b);
 }
-
-// (A CTA variant with the vehicles' sweeps in lock step, as in K_solve, measured SLOWER here - 427 k vs 702 k
-// vehicle-steps/s at N = 15: closed-loop steps are short warm-started solves dominated by setup and factorisation,
-// and the small footprint lets 15 independent warps share an SM.)
 
 // ------------------------------------------------------------------------------------------------
 // K_ref: batched build_reference (src/control/ref_builder.py:10-22 + src/common/geometry.py:9-45), one thread per path:
@@ -323,8 +289,8 @@ struct cudampc_handle {
   // staging for the host-pointer entry point
   double *h_in, *h_out, *d_in, *d_out;
   size_t in_doubles, out_doubles;
-  int sms, per_sm, smem_bytes;
-  int cta_P, cta_smem, cta_chunk, use_cta, cta_wpp, warp_per_sm;
+  int sms, smem_bytes, roll_per_sm;   // K_rollout: one-warp CTAs of smem_bytes each, roll_per_sm resident per SM
+  int grp_P, grp_wpp, grp_smem;        // K_solve: one CTA per SM with grp_P groups of grp_wpp warps
   long long launches;
   char err[512];
 };
@@ -431,36 +397,30 @@ int cudampc_create(const cudampc_params* params, int max_batch, int device, cuda
   cudaError_t e = cudaGetDeviceProperties(&prop, device);
   if (e != cudaSuccess) { delete h; return fail(nullptr, CUDAMPC_ERR_CUDA, "CUDA failure: %s", cudaGetErrorString(e)); }
   h->sms = prop.multiProcessorCount;
-  h->smem_bytes = footprint(p.N) * (int)sizeof(double);
+  const int F = footprint(p.N);
+  h->smem_bytes = F * (int)sizeof(double);
   const int optin = (int)prop.sharedMemPerBlockOptin;
-  if (h->smem_bytes > optin) { delete h; return fail(nullptr, CUDAMPC_ERR_UNSUPPORTED, "%s", "horizon too long for one problem per 227 KB of shared memory"); }
-  e = cudaFuncSetAttribute(mpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(mpc_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes);
+  if (h->smem_bytes + (int)sizeof(GroupShared) > optin) { delete h; return fail(nullptr, CUDAMPC_ERR_UNSUPPORTED, "%s", "horizon too long for one problem per 227 KB of shared memory"); }
+  // K_rollout: one-warp CTAs
+  e = cudaFuncSetAttribute(mpc_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes);
   int occ = 0;
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mpc_solve_kernel, 32, h->smem_bytes);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mpc_rollout_kernel, 32, h->smem_bytes);
   if (e != cudaSuccess || occ < 1) { delete h; return fail(nullptr, CUDAMPC_ERR_CUDA, "CUDA failure: %s", cudaGetErrorString(e)); }
-  h->per_sm = occ;
-  h->warp_per_sm = occ;
-  // transposed-chain kernel: one CTA per SM holding P problems (P <= 16: 512 threads x 128 registers)
+  h->roll_per_sm = occ;
+  // K_solve: one CTA per SM with P independent groups.  P <= 8: with more resident warps the 255-register budget of the
+  // driver would have to shrink.  Two warps per group pay off only when few problems fit (long horizons: the SM is
+  // latency-bound there); at P >= 3 the sub-partitions are issue-bound and the extra barriers cost more than they save.
   {
-    const int F = footprint(p.N);
-    int P = (optin - (int)sizeof(CtaShared) - 64) / (F * (int)sizeof(double));
-    if (P > 8) P = 8;          // 8 problems = 16 chain lanes; beyond that the 128-register budget of a 512-thread CTA spills (measured slower)
-    if (const char* pe = getenv("CUDAMPC_P")) { int v = atoi(pe); if (v >= 1 && v < P) P = v; }   // tuning knob
-    h->cta_P = P;
-    h->cta_smem = P * F * (int)sizeof(double) + (int)sizeof(CtaShared) + 16;
-    h->cta_chunk = (half_bot(p.N) + 1) / 2;  // a (twisted) factorisation spreads over 2 rounds
-    const char* env = getenv("CUDAMPC_KERNEL");
-    h->use_cta = (P >= 2) && !(env && strcmp(env, "warp") == 0);
-    if (h->use_cta) {
-      const char* we = getenv("CUDAMPC_WPP");
-      h->cta_wpp = (P <= 6 && p.N + 1 > 32 && !(we && atoi(we) == 1)) ? 2 : 1;   // two warps per problem pay off once a problem has more than 32 stages
-      e = h->cta_wpp == 2 ? cudaFuncSetAttribute(mpc_solve_cta_kernel<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta_smem)
-          : (P <= 8) ? cudaFuncSetAttribute(mpc_solve_cta_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta_smem)
-                     : cudaFuncSetAttribute(mpc_solve_cta_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta_smem);
-      if (e != cudaSuccess) { delete h; return fail(nullptr, CUDAMPC_ERR_CUDA, "CUDA failure: %s", cudaGetErrorString(e)); }
-      h->per_sm = P;
-    }
+    int P = (optin - 64) / (F * (int)sizeof(double) + (int)sizeof(GroupShared));
+    if (P > 8) P = 8;            // measured at N=20: 12 groups under a 168-register cap gain 5 % without early polish, lose 15 % with it
+    if (const char* pe = getenv("CUDAMPC_P")) { int v = atoi(pe); if (v >= 1 && v < P) P = v; }   // tuning knobs
+    h->grp_P = P;
+    h->grp_wpp = (P <= 2 && p.N + 1 > 32) ? 2 : 1;
+    if (const char* we = getenv("CUDAMPC_WPP")) { int v = atoi(we); if (v == 1 || (v == 2 && P <= 2)) h->grp_wpp = v; }
+    h->grp_smem = P * (F * (int)sizeof(double) + (int)sizeof(GroupShared)) + 16;
+    e = h->grp_wpp == 2 ? cudaFuncSetAttribute(mpc_solve_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->grp_smem)
+                        : cudaFuncSetAttribute(mpc_solve_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->grp_smem);
+    if (e != cudaSuccess) { delete h; return fail(nullptr, CUDAMPC_ERR_CUDA, "CUDA failure: %s", cudaGetErrorString(e)); }
   }
   const size_t ws = (size_t)warm_size(p.N) * max_batch * sizeof(double);
   const size_t wk = (size_t)(16 + 4 * (p.N + 1) + 2 * p.N) * max_batch * sizeof(double);
@@ -528,7 +488,7 @@ double cudampc_fp64_peak_tflops(cudampc_handle* h) {
 }
 
 int cudampc_workspace_doubles(const cudampc_handle* h) { return h ? footprint(h->N) : 0; }
-int cudampc_problems_per_sm(const cudampc_handle* h) { return h ? h->per_sm : 0; }
+int cudampc_problems_per_sm(const cudampc_handle* h) { return h ? h->grp_P : 0; }
 int64_t cudampc_launch_count(const cudampc_handle* h) { return h ? h->launches : 0; }
 
 int cudampc_linearize_batch(cudampc_handle* h, int batch, const double* ref_dev, double* A_dev, double* B_dev,
@@ -566,17 +526,11 @@ int cudampc_solve_batch(cudampc_handle* h, int batch, const double* x0_dev, cons
   a.x0 = x0_dev; a.ref = ref_dev; a.u_prev = u_prev_dev; a.warm = h->warm; a.scratch = h->scratch;
   a.u0 = u0_dev; a.Xp = Xp_dev; a.Up = Up_dev; a.status = status_dev; a.iters = iters_dev;
   a.pri = pri_res_dev; a.dua = dua_res_dev; a.info = info_dev; a.counter = h->counter; a.batch = batch;
-  if (h->use_cta) {
-    int grid = (batch + h->cta_P - 1) / h->cta_P;
-    if (grid > h->sms) grid = h->sms;
-    if (h->cta_wpp == 2) mpc_solve_cta_kernel<384, 2><<<grid, 64 * h->cta_P, h->cta_smem, st>>>(h->p, s, a, h->cta_P, footprint(h->N), h->cta_chunk);
-    else if (h->cta_P <= 8) mpc_solve_cta_kernel<256, 1><<<grid, 32 * h->cta_P, h->cta_smem, st>>>(h->p, s, a, h->cta_P, footprint(h->N), h->cta_chunk);
-    else mpc_solve_cta_kernel<512, 1><<<grid, 32 * h->cta_P, h->cta_smem, st>>>(h->p, s, a, h->cta_P, footprint(h->N), h->cta_chunk);
-  } else {
-    int grid = h->sms * h->warp_per_sm;
-    if (grid > batch) grid = batch;
-    mpc_solve_kernel<<<grid, 32, h->smem_bytes, st>>>(h->p, s, a);
-  }
+  int grid = (batch + h->grp_P - 1) / h->grp_P;
+  if (grid > h->sms) grid = h->sms;
+  const int threads = 32 * h->grp_wpp * h->grp_P;
+  if (h->grp_wpp == 2) mpc_solve_kernel<128, 2><<<grid, threads, h->grp_smem, st>>>(h->p, s, a, h->grp_P, footprint(h->N));
+  else mpc_solve_kernel<256, 1><<<grid, threads, h->grp_smem, st>>>(h->p, s, a, h->grp_P, footprint(h->N));
   h->launches++;
   CU(h, cudaGetLastError());
   return CUDAMPC_OK;
@@ -693,7 +647,7 @@ int cudampc_rollout_batch(cudampc_handle* h, int batch, const double* ref_global
   a.states = states_dev; a.controls = controls_dev; a.n_steps = n_steps_dev; a.flags = flags_dev;
   a.step_status = step_status_dev; a.step_iters = step_iters_dev; a.counter = h->counter; a.batch = batch;
   {
-    int grid = h->sms * h->warp_per_sm;
+    int grid = h->sms * h->roll_per_sm;
     if (grid > batch) grid = batch;
     mpc_rollout_kernel<<<grid, 32, h->smem_bytes, st>>>(h->p, s, c, a);
   }

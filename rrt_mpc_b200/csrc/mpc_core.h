@@ -116,6 +116,7 @@ MPC_HD void layout_pads(int N, int P, int& fpad, int& xpad) {
   fpad = 2 * ((want - nat) & 7);
   xpad = ((7 * (half_top(N) + 2)) & 1) ? 0 : 1;                // make the bottom rows' offset odd
 }
+MPC_HD void layout_pads(int N, int& fpad, int& xpad) { layout_pads(N, 1, fpad, xpad); }   // one problem per chain warp
 // warm-start state kept in HBM between calls: per stage xu(6) s(5) v(15) ye(4), + yi(4) + rho
 MPC_HD int warm_size(int N) { return 30 * (N + 1) + 5; }
 

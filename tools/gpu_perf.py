@@ -20,5 +20,5 @@ for _ in range(3):
     best = min(best, e0.elapsed_time(e1))
 it = r.iters.double().mean().item()
 cyc = best * 1e-3 / (B * it) * 148 * 1.8e9
-print(f"[{os.environ.get('CUDAMPC_KERNEL','cta')}] N={N} B={B} per_sm={ctl.problems_per_sm()}: {best:.2f} ms -> {B/best*1e3:.0f} solves/s, mean iters {it:.1f}, "
+print(f"[group] N={N} B={B} per_sm={ctl.problems_per_sm()}: {best:.2f} ms -> {B/best*1e3:.0f} solves/s, mean iters {it:.1f}, "
       f"{cyc:.0f} SM-cycles per problem-iteration, solved {(r.status==1).sum().item()}")

@@ -38,3 +38,26 @@ for r in data:
 print(f"total inst {ti:.3g} samples {ts:.0f}")
 for l, (n, s, ops) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
     print(f"{str(l):40s} inst {100*n/ti:5.1f}%  samples {100*s/ts:5.1f}%   {dict(ops.most_common(4))}")
+# per-function summary: map (file, line) -> enclosing function via a crude scan of the sources
+import bisect
+csrc = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "rrt_mpc_b200", "csrc")
+fmap = {}
+for fn in os.listdir(csrc):
+    starts = []
+    for i, ln in enumerate(open(os.path.join(csrc, fn)), 1):
+        m = re.match(r"(?:template\s*<[^>]*>\s*)?(?:MPC_HD|__device__|__global__|static|inline)[^;(]*?([A-Za-z_0-9]+)\s*\(", ln)
+        if m: starts.append((i, m.group(1)))
+    fmap[fn] = starts
+reg = collections.defaultdict(lambda: [0.0, 0.0, 0.0])
+F64 = {"DFMA", "DMUL", "DADD", "DSETP", "DMNMX"}
+for l, (n, s, ops) in agg.items():
+    name = "?"
+    if l and l[0] in fmap and fmap[l[0]]:
+        st = fmap[l[0]]; j = bisect.bisect_right([a for a, _ in st], l[1]) - 1
+        name = f"{l[0]}:{st[j][1]}" if j >= 0 else l[0]
+    elif l: name = l[0]
+    reg[name][0] += n; reg[name][1] += s; reg[name][2] += n + sum(v for k, v in ops.items() if k in F64)
+tot_issue = sum(v[2] for v in reg.values())
+print("\nper function: inst%, samples%, issue-slot% (fp64 counted twice)")
+for name, (n, s, iss) in sorted(reg.items(), key=lambda kv: -kv[1][2])[:30]:
+    print(f"{name:45s} inst {100*n/ti:5.1f}%  samples {100*s/ts:5.1f}%  issue {100*iss/tot_issue:5.1f}%")
