@@ -94,11 +94,12 @@ enum { BLK = 44 };
 MPC_HD int mid_stage(int N) { return N / 2; }
 MPC_HD int half_top(int N) { return mid_stage(N) + 1; }          // local stages of the top half (last = middle = border)
 MPC_HD int half_bot(int N) { return N - mid_stage(N) + 1; }      // local stages of the bottom half (last = middle = border)
-MPC_HD int bx_doubles(int N) { return 7 * (half_top(N) + 2) + 7 * (half_bot(N) + 2) + 1; }
-MPC_HD int band_offset(int N) {           // even => 16-byte aligned blocks
-  int o = hdr_size(N) + (N + 1) * SR + bx_doubles(N);
-  return (o + 1) & ~1;
-}
+// rhs/solution rows: BXS = 6 doubles per local stage, rows -1 .. H of each half, 16-byte aligned so that the chain moves a
+// row with three 128-bit accesses (shared-memory instructions, not bytes, are what the chain warp pays for)
+enum { BXS = 6 };
+MPC_HD int bx_offset(int N) { return (hdr_size(N) + (N + 1) * SR + 1) & ~1; }
+MPC_HD int bx_doubles(int N) { return BXS * (half_top(N) + 2) + BXS * (half_bot(N) + 2) + 2; }
+MPC_HD int band_offset(int N) { return bx_offset(N) + bx_doubles(N); }   // even => 16-byte aligned blocks
 enum { PAD_MAX = 16 };                     // room for the bank-conflict pads of the bottom half (fpad, xpad)
 MPC_HD int footprint(int N) {
   int f = band_offset(N) + BLK * (half_top(N) + 1) + BLK * (half_bot(N) + 1) + 22 + PAD_MAX + 2;
@@ -114,7 +115,7 @@ MPC_HD void layout_pads(int N, int P, int& fpad, int& xpad) {
   const int nat = ((BLK * (half_top(N) + 1)) / 2) & 7;         // natural column offset of the bottom half
   const int want = (P * q) & 7;
   fpad = 2 * ((want - nat) & 7);
-  xpad = ((7 * (half_top(N) + 2)) & 1) ? 0 : 1;                // make the bottom rows' offset odd
+  xpad = (((BXS * (half_top(N) + 2)) / 2) & 1) ? 0 : 2;         // bottom rows an odd number of 16-byte columns from the top rows
 }
 MPC_HD void layout_pads(int N, int& fpad, int& xpad) { layout_pads(N, 1, fpad, xpad); }   // one problem per chain warp
 // warm-start state kept in HBM between calls: per stage xu(6) s(5) v(15) ye(4), + yi(4) + rho
@@ -123,7 +124,7 @@ MPC_HD int warm_size(int N) { return 30 * (N + 1) + 5; }
 // one half of the twisted system as the chain code sees it (local stage index i = 0 .. H-1, border = H-1)
 struct HalfView {
   double* bx0; double* blk0; int H;
-  MPC_HD double* bx(int i) const { return bx0 + 7 * i; }         // i = -1 .. H
+  MPC_HD double* bx(int i) const { return bx0 + BXS * i; }       // i = -1 .. H
   MPC_HD double* blk(int i) const { return blk0 + BLK * i; }     // i = 0 .. H
 };
 
@@ -134,11 +135,11 @@ struct View {
   MPC_HD double* hdr() const { return base; }
   MPC_HD int* act() const { return reinterpret_cast<int*>(base + H_ACT); }  // [N+1] stage masks + [N+1]=init rows
   MPC_HD double* rec(int k) const { return base + hdr_size(N) + k * SR; }
-  MPC_HD double* bx_base() const { return base + hdr_size(N) + (N + 1) * SR; }
+  MPC_HD double* bx_base() const { return base + bx_offset(N); }
   MPC_HD double* scratch() const { return bx_base(); }                       // >= N+1 doubles, free before the first solve
-  MPC_HD HalfView top() const { return HalfView{bx_base() + 7, base + band_offset(N), half_top(N)}; }
+  MPC_HD HalfView top() const { return HalfView{bx_base() + BXS, base + band_offset(N), half_top(N)}; }
   MPC_HD HalfView bottom() const {
-    return HalfView{bx_base() + 7 * (half_top(N) + 2) + 7 + xpad, base + band_offset(N) + BLK * (half_top(N) + 1) + fpad, half_bot(N)};
+    return HalfView{bx_base() + BXS * (half_top(N) + 2) + BXS + xpad, base + band_offset(N) + BLK * (half_top(N) + 1) + fpad, half_bot(N)};
   }
   MPC_HD double* mid() const { return base + band_offset(N) + BLK * (half_top(N) + 1) + BLK * (half_bot(N) + 1) + PAD_MAX; }
   // element (k, j) of the right-hand side / solution vector in the twisted storage
@@ -592,17 +593,17 @@ MPC_HD void chain_load_fwd(const HalfView& h, int k, ChainRegs& r) {
   const D2* __restrict__ pc = reinterpret_cast<const D2*>(h.blk(k + 1) + 22);
 #pragma unroll
   for (int i = 0; i < 11; ++i) { D2 u = pa[i], v = pc[i]; r.la[2 * i] = u.x; r.la[2 * i + 1] = u.y; r.lc[2 * i] = v.x; r.lc[2 * i + 1] = v.y; }
-  const double* bn = h.bx(k + 1);
+  const D2* __restrict__ bn = reinterpret_cast<const D2*>(h.bx(k + 1));
 #pragma unroll
-  for (int j = 0; j < 6; ++j) r.nb[j] = bn[j];
+  for (int i = 0; i < 3; ++i) { D2 u = bn[i]; r.nb[2 * i] = u.x; r.nb[2 * i + 1] = u.y; }
 }
 MPC_HD void chain_load_bwd(const HalfView& h, int k, ChainRegs& r) {
   const D2* __restrict__ pa = reinterpret_cast<const D2*>(h.blk(k));
 #pragma unroll
   for (int i = 0; i < 11; ++i) { D2 u = pa[i], v = pa[11 + i]; r.la[2 * i] = u.x; r.la[2 * i + 1] = u.y; r.lc[2 * i] = v.x; r.lc[2 * i + 1] = v.y; }
-  const double* bp = h.bx(k - 1);
+  const D2* __restrict__ bp = reinterpret_cast<const D2*>(h.bx(k - 1));
 #pragma unroll
-  for (int j = 0; j < 6; ++j) r.nb[j] = bp[j];
+  for (int i = 0; i < 3; ++i) { D2 u = bp[i]; r.nb[2 * i] = u.x; r.nb[2 * i + 1] = u.y; }
 }
 MPC_HD void chain_math_fwd(const ChainRegs& r, double* a, double* out) {
   double nx[6];
@@ -637,8 +638,9 @@ MPC_HD void chain_math_bwd(const ChainRegs& r, double* a, double* out) {
   for (int j = 0; j < 6; ++j) a[j] = nx[j];
 }
 MPC_HD void chain_store(double* bk, const double* out) {
+  D2* q = reinterpret_cast<D2*>(bk);
 #pragma unroll
-  for (int j = 0; j < 6; ++j) bk[j] = out[j];
+  for (int i = 0; i < 3; ++i) { D2 u; u.x = out[2 * i]; u.y = out[2 * i + 1]; q[i] = u; }
 }
 
 // Forward sweep of one half over its local stages 0..H-2; returns the accumulators of the border stage in a[].

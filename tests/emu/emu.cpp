@@ -68,7 +68,7 @@ int emu_solve_batch(const double* par, const double* set, int N, int B, int reve
   std::vector<double> ws(footprint(N)), scratch(warm_size(N)), warm_local(warm_size(N));
   for (int b = 0; b < B; ++b) {
     std::fill(ws.begin(), ws.end(), 0.0);
-    View w{ws.data(), N, 4, 1};   // arbitrary non-zero pads: the layout must work with any
+    View w{ws.data(), N, 4, 2};   // arbitrary non-zero (even: 16-byte aligned) pads: the layout must work with any
     ProblemIO io;
     io.x0 = x0 + 4 * b; io.ref = RefWin{ref + (size_t)4 * (N + 1) * b, 0, N + 1, 1.0}; io.u_prev = u_prev ? u_prev + 2 * b : nullptr;
     io.warm = warm ? warm + (size_t)warm_size(N) * b : warm_local.data();
