@@ -39,9 +39,9 @@ EARLY_POLISH = 1          # finish as soon as a polish certifies a KKT point of 
 # canonical flop model of BASELINE.md §2 / SURVEY.md §8d (n = 11N+5, m = 19N+7, nnz(A) = 43N+5)
 _NNZ_L = {15: 706, 20: 941, 50: 2349}
 # DRAM traffic per solve of K_solve from the ncu --set full capture profiles/ncu_full_r01_solve_summary.txt
-# (dram__bytes_read.sum + dram__bytes_write.sum = 74.78 MB for a 4,096-problem launch): dominated by the
+# (dram__bytes_read.sum + dram__bytes_write.sum = 8.49 + 56.18 MB for a 4,096-problem launch): dominated by the
 # warm-start / polish back-up of the ADMM iterate (12 KB per save), not by the 4.1 KB of algorithmic I/O.
-TRAFFIC_BYTES_PER_SOLVE = 74.78e6 / 4096
+TRAFFIC_BYTES_PER_SOLVE = 64.67e6 / 4096
 
 
 def flop_model(N: int):
