@@ -103,12 +103,13 @@ MPC_HD int band_offset(int N) { return bx_offset(N) + bx_doubles(N); }   // even
 enum { PAD_MAX = 16 };                     // room for the bank-conflict pads of the bottom half (fpad, xpad)
 MPC_HD int footprint(int N) {
   int f = band_offset(N) + BLK * (half_top(N) + 1) + BLK * (half_bot(N) + 1) + 22 + PAD_MAX + 2;
-  while ((f & 3) != 2) ++f;               // F = 2 (mod 4): conflict-free 128-bit loads when lanes stride over problems
+  while ((f & 3) != 2) ++f;               // F = 2 (mod 4): 16-byte aligned, and an odd number of 16-byte columns per problem
   return f;
 }
-// Pads that make the chain warp's accesses conflict-free when lanes 0..P-1 read top halves and lanes P..2P-1 bottom
-// halves of P problems F doubles apart: the bottom half's factor blocks are shifted by P 16-byte columns (mod 8)
-// relative to the top half's, its rhs/solution rows by an odd number of 8-byte bank pairs.
+// Pads that make the chain warp's accesses bank-conflict-free.  General form: lanes 0..P-1 read top halves and lanes
+// P..2P-1 bottom halves of P problems F doubles apart (what tools/microbench/chain_bench.cu sweeps); the kernels use
+// P = 1: lane 0 = top half, lane 1 = bottom half of the warp's own problem.  The bottom half's factor blocks are shifted
+// by P 16-byte columns (mod 8) relative to the top half's, its rhs/solution rows by an odd number of 16-byte columns.
 MPC_HD void layout_pads(int N, int P, int& fpad, int& xpad) {
   const int F = footprint(N);
   const int q = (F / 2) & 7;                                   // 16-byte columns per problem (odd)
@@ -643,11 +644,73 @@ MPC_HD void chain_store(double* bk, const double* out) {
   for (int i = 0; i < 3; ++i) { D2 u; u.x = out[2 * i]; u.y = out[2 * i + 1]; q[i] = u; }
 }
 
+// Rolling variant (MODE 2): the in-stage arithmetic (pivot chain) and the cross arithmetic (feeds the next stage) are
+// separated and each part's registers are refilled for the next stage as soon as the part is done.  Same operations in
+// the same order per accumulator as the interleaved form: bit-identical results.
+MPC_HD void chain_load_in(const double* blk, double* la) {
+  const D2* __restrict__ pa = reinterpret_cast<const D2*>(blk);
+#pragma unroll
+  for (int i = 0; i < 11; ++i) { D2 u = pa[i]; la[2 * i] = u.x; la[2 * i + 1] = u.y; }
+}
+MPC_HD void chain_load_cross(const double* blk, const double* bx, double* lc, double* nb) {
+  const D2* __restrict__ pc = reinterpret_cast<const D2*>(blk + 22);
+#pragma unroll
+  for (int i = 0; i < 11; ++i) { D2 v = pc[i]; lc[2 * i] = v.x; lc[2 * i + 1] = v.y; }
+  const D2* __restrict__ pb = reinterpret_cast<const D2*>(bx);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { D2 v = pb[i]; nb[2 * i] = v.x; nb[2 * i + 1] = v.y; }
+}
+MPC_HD void chain_in_fwd(const double* la, double* a, double* out) {
+#pragma unroll
+  for (int jp = 0; jp < 6; ++jp) {
+    const double wv = a[jp];
+    out[jp] = wv * la[MPC_ID(jp)];
+#pragma unroll
+    for (int j = jp + 1; j < 6; ++j) a[j] = fma(-la[MPC_IA(j, jp)], wv, a[j]);
+  }
+}
+MPC_HD void chain_cross_fwd(const double* lc, const double* nb, double* a) {
+  double nx[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) nx[j] = nb[j];
+#pragma unroll
+  for (int jp = 0; jp < 6; ++jp)
+#pragma unroll
+    for (int j = 0; j <= jp; ++j) nx[j] = fma(-lc[MPC_IC(j, jp) - 22], a[jp], nx[j]);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) a[j] = nx[j];
+}
+MPC_HD void chain_in_bwd(const double* la, double* a, double* out) {
+#pragma unroll
+  for (int jp = 5; jp >= 0; --jp) {
+    const double xv = a[jp];
+    out[jp] = xv;
+#pragma unroll
+    for (int j = jp - 1; j >= 0; --j) a[j] = fma(-la[MPC_IA(jp, j)], xv, a[j]);
+  }
+}
+MPC_HD void chain_cross_bwd(const double* lc, const double* nb, double* a) {
+  double nx[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) nx[j] = nb[j];
+#pragma unroll
+  for (int jp = 5; jp >= 0; --jp)
+#pragma unroll
+    for (int j = 5; j >= jp; --j) nx[j] = fma(-lc[MPC_IC(jp, j) - 22], a[jp], nx[j]);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) a[j] = nx[j];
+}
+// one stage of the rolling sweeps; `d` = +1 forward, -1 backward
+#define MPC_ROLL_FWD(k) { chain_in_fwd(r0.la, a, out); chain_load_in(h.blk((k) + 1), r0.la); chain_cross_fwd(r0.lc, r0.nb, a); \
+                          chain_load_cross(h.blk((k) + 2), h.bx((k) + 2), r0.lc, r0.nb); chain_store(h.bx(k), out); }
+#define MPC_ROLL_BWD(k) { chain_in_bwd(r0.la, a, out); chain_load_in(h.blk((k) - 1), r0.la); chain_cross_bwd(r0.lc, r0.nb, a); \
+                          chain_load_cross(h.blk((k) - 1), h.bx((k) - 2), r0.lc, r0.nb); chain_store(h.bx(k), out); }
+
 // Forward sweep of one half over its local stages 0..H-2; returns the accumulators of the border stage in a[].
 // PIPE = true: software-pipelined by hand (two register sets, loop unrolled by two): the loads of stage k+1 are
 // issued BEFORE the arithmetic and the stores of stage k (the compiler cannot do this itself because it must
 // assume the stores alias the next loads); ~190 registers.  PIPE = false: one register set (~80 registers).
-template <bool PIPE>
+template <int PIPE>
 MPC_HD void half_forward(const HalfView& h, double* a) {
   const int last = h.H - 2;                 // last eliminated local stage
   double out[6];
@@ -657,7 +720,14 @@ MPC_HD void half_forward(const HalfView& h, double* a) {
 #pragma unroll
     for (int j = 0; j < 6; ++j) a[j] = b0[j];
   }
-  if (PIPE) {
+  if (PIPE == 2) {                          // (refills past the end read the border / padding block and row H: unused)
+    if (last < 0) return;
+    chain_load_in(h.blk(0), r0.la);
+    chain_load_cross(h.blk(1), h.bx(1), r0.lc, r0.nb);
+    int k = 0;
+    for (; k + 1 <= last; k += 2) { MPC_ROLL_FWD(k); MPC_ROLL_FWD(k + 1); }
+    if (k <= last) MPC_ROLL_FWD(k);
+  } else if (PIPE == 1) {
     ChainRegs r1;
     if (last >= 0) chain_load_fwd(h, 0, r0);
     int k = 0;
@@ -683,14 +753,20 @@ MPC_HD void half_forward(const HalfView& h, double* a) {
 }
 // Backward sweep of one half from the border (whose solution xm, in the half's local index order, is given and
 // whose in-stage factor part is zero) down to local stage 0.
-template <bool PIPE>
+template <int PIPE>
 MPC_HD void half_backward(const HalfView& h, const double* xm) {
   double a[6], out[6];
   ChainRegs r0;
 #pragma unroll
   for (int j = 0; j < 6; ++j) a[j] = xm[j];
   const int first = h.H - 1;
-  if (PIPE) {
+  if (PIPE == 2) {                          // (refills below stage 0 read in-bounds words of this problem's workspace: unused)
+    chain_load_in(h.blk(first), r0.la);
+    chain_load_cross(h.blk(first), h.bx(first - 1), r0.lc, r0.nb);
+    int k = first;
+    for (; k - 1 >= 0; k -= 2) { MPC_ROLL_BWD(k); MPC_ROLL_BWD(k - 1); }
+    if (k >= 0) MPC_ROLL_BWD(k);
+  } else if (PIPE == 1) {
     ChainRegs r1;
     chain_load_bwd(h, first, r0);
     int k = first;
@@ -715,17 +791,20 @@ MPC_HD void half_backward(const HalfView& h, const double* xm) {
   }
 }
 // whole twisted solve, sequential (host emulation / single-lane use): L D L' x = b in place on the bx storage
-MPC_HD void chain_solve(const View& w) {
+template <int MODE>
+MPC_HD void chain_solve_mode(const View& w) {
   HalfView T = w.top(), B = w.bottom();
   double aT[6], aB[6], xm[6], xr[6];
-  half_forward<false>(T, aT);
-  half_forward<false>(B, aB);
+  half_forward<MODE>(T, aT);
+  half_forward<MODE>(B, aB);
   for (int j = 0; j < 6; ++j) aT[j] += aB[5 - j];
   middle_solve(w, aT, xm);
   for (int j = 0; j < 6; ++j) xr[j] = xm[5 - j];
-  half_backward<false>(T, xm);
-  half_backward<false>(B, xr);
+  half_backward<MODE>(T, xm);
+  half_backward<MODE>(B, xr);
 }
+MPC_HD void chain_solve(const View& w) { chain_solve_mode<0>(w); }
+MPC_HD void chain_solve_rolling(const View& w) { chain_solve_mode<2>(w); }   // the kernel's hot-loop order of loads
 
 // ----------------------------------------------------------------------------------------------
 // ADMM step, split in two stage-parallel halves

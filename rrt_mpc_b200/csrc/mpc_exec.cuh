@@ -8,7 +8,7 @@ namespace mpc {
 
 // One lane sweeps one half of one problem: `bottom` selects the half, `partner` is the lane that holds the other
 // half of the same problem.  Called by ALL 32 lanes of the warp (inactive lanes only take part in the shuffles).
-template <bool PIPE>
+template <int PIPE>
 __device__ __forceinline__ void chain_twisted_lanes(bool active, bool bottom, int partner, const View& w) {
   double a[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, o[6], xm[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   const HalfView h = bottom ? w.bottom() : w.top();
@@ -29,8 +29,8 @@ __device__ __forceinline__ void chain_twisted_lanes(bool active, bool bottom, in
 }
 // twisted factorisation of local stages [i0, i1) of both halves by two lanes; `last` also forms the middle block
 __device__ __forceinline__ void factor_twisted_lanes(int lane, const View& w, int i0, int i1, bool last) {
-  if (lane == 0) factor_half(w.top(), i0, i1);
-  else if (lane == 1) factor_half(w.bottom(), i0, i1);
+  const HalfView h = lane == 1 ? w.bottom() : w.top();
+  if (lane < 2) factor_half(h, i0, i1);            // ONE instruction stream for both halves (two branches would serialise them)
   __syncwarp();
   if (last && lane == 0) factor_middle(w);
   __syncwarp();
@@ -113,8 +113,12 @@ struct GroupExec {
     return b;
   }
   // callers reach solve()/factor() right after a phase's group_sync, so the right-hand side / band is visible
-  __device__ __forceinline__ void solve(const View& w) {
-    if (chain_warp()) chain_twisted_lanes<false>(lane < 2, lane == 1, lane ^ 1, w);
+  __device__ __forceinline__ void solve(const View& w) {           // polish / refinement solves: compact code
+    if (chain_warp()) chain_twisted_lanes<0>(lane < 2, lane == 1, lane ^ 1, w);
+    group_sync();
+  }
+  __device__ __forceinline__ void solve_iter(const View& w) {      // the solve of every ADMM iteration: rolling prefetch
+    if (chain_warp()) chain_twisted_lanes<2>(lane < 2, lane == 1, lane ^ 1, w);
     group_sync();
   }
   __device__ __forceinline__ void factor(const View& w) {

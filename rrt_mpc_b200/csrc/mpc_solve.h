@@ -156,7 +156,7 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
   bool finished = false, need_restore = false;
   while (!finished) {
     ++it;
-    ex.tag(1); ex.solve(w); ++n_solve;
+    ex.tag(1); ex.solve_iter(w); ++n_solve;
     ex.tag(2); ex.stages(NS, [&](int k) { admm_update_fast(w, p, ic, k); });
     const bool last = it >= s.max_iter;
     const bool check = last || ((s.check_termination > 0) && (it % s.check_termination == 0));

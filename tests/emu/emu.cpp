@@ -28,6 +28,7 @@ struct EmuExec {
   }
   void factor(const View& w) { factor_band(w); }
   void solve(const View& w) { chain_solve(w); }
+  void solve_iter(const View& w) { chain_solve_rolling(w); }   // same arithmetic, the kernel's prefetch order
 };
 
 extern "C" {

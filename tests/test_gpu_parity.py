@@ -140,7 +140,8 @@ def test_ragged_batch_sizes_and_device_path(B):
     assert np.array_equal(r0.u0, rz.u0)
 
 
-@pytest.mark.parametrize("N", [1, 2, 7, 33, 64])
+# 100 / 150: only two problems / one problem fit an SM -> the two-warps-per-problem instantiation of K_solve
+@pytest.mark.parametrize("N", [1, 2, 7, 33, 64, 100, 150])
 def test_horizon_edge_cases(N):
     from oracle import mpc_numpy as O
     p = oracle_params(N)

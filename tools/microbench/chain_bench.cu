@@ -12,7 +12,7 @@ __device__ void fill(const View& w) {
   for (int s = 0; s < 2; ++s)
     for (int k = 0; k <= hs[s].H; ++k) { double* b = hs[s].blk(k); for (int d = 0; d < 44; ++d) b[d] = 0.01 * ((k + d) % 7); for (int j = 0; j < 6; ++j) b[15 + j] = 4.0 + (k % 3); }
 }
-template <bool PIPE>
+template <int PIPE>
 __global__ void bench(int N, int F, int P, int reps, long long* cyc, double* sink) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;
@@ -44,15 +44,16 @@ int main(int argc, char** argv) {
   int F = footprint(N);
   long long* cyc; double* sink;
   CK(cudaMalloc(&cyc, 16)); CK(cudaMalloc(&sink, 148 * 32 * 8));
-  CK(cudaFuncSetAttribute(bench<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CK(cudaFuncSetAttribute(bench<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CK(cudaFuncSetAttribute(bench<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CK(cudaFuncSetAttribute(bench<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CK(cudaFuncSetAttribute(bench<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   int maxl = (227 * 1024) / (F * 8);
   if (maxl > 16) maxl = 16;
-  int ls[] = {1, 2, 4, 5, 8, 12, 16};
-  for (int pipe = 0; pipe < 2; ++pipe)
-    for (int li = 0; li < 7; ++li) {
+  int ls[] = {1, 2, 5};
+  for (int pipe = 0; pipe < 3; ++pipe)
+    for (int li = 0; li < 3; ++li) {
       int P = ls[li]; if (P > maxl) continue;
-      if (pipe) bench<true><<<148, 64, P * F * 8>>>(N, F, P, 20, cyc, sink); else bench<false><<<148, 64, P * F * 8>>>(N, F, P, 20, cyc, sink);
+      if (pipe == 2) bench<2><<<148, 64, P * F * 8>>>(N, F, P, 20, cyc, sink); else if (pipe) bench<1><<<148, 64, P * F * 8>>>(N, F, P, 20, cyc, sink); else bench<0><<<148, 64, P * F * 8>>>(N, F, P, 20, cyc, sink);
       CK(cudaDeviceSynchronize());
       long long h[2]; CK(cudaMemcpy(h, cyc, 16, cudaMemcpyDeviceToHost));
       printf("N=%d P=%2d pipe=%d: twisted solve %lld cycles (%.1f per stage-pass of a half), sequential factor %lld cycles\n", N, P, pipe, h[0], h[0] / (2.0 * (half_bot(N) - 1)), h[1]);

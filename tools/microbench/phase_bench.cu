@@ -20,6 +20,7 @@ struct TimedExec {
   template <class F> __device__ __forceinline__ int any(int n, F f) { int a = 0; for (int k = lane; k < n; k += 32) a |= f(k); a = __any_sync(0xffffffffu, a); __syncwarp(); return a; }
   __device__ __forceinline__ void factor(const View& w) { if (lane == 0) factor_band(w); __syncwarp(); }
   __device__ __forceinline__ void solve(const View& w) { if (lane == 0) chain_solve(w); __syncwarp(); }
+  __device__ __forceinline__ void solve_iter(const View& w) { solve(w); }
 };
 __global__ void k(Params p, Settings s, const double* x0, const double* ref, const double* up, double* warm, double* out, long long* cyc, int* cnt, int* iters) {
   extern __shared__ double smem[];
