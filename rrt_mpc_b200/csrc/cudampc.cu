@@ -656,4 +656,12 @@ int cudampc_rollout_batch(cudampc_handle* h, int batch, const double* ref_global
   return CUDAMPC_OK;
 }
 
+#ifdef MPC_TIMING
+int cudampc_debug_tag_cycles(unsigned long long* out16, int reset) {
+  if (cudaMemcpyFromSymbol(out16, g_tag_cycles, sizeof(unsigned long long) * 16) != cudaSuccess) return CUDAMPC_ERR_CUDA;
+  if (reset) { unsigned long long z[16] = {0}; if (cudaMemcpyToSymbol(g_tag_cycles, z, sizeof z) != cudaSuccess) return CUDAMPC_ERR_CUDA; }
+  return CUDAMPC_OK;
+}
+#endif
+
 }  // extern "C"

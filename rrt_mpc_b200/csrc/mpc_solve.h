@@ -110,6 +110,7 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
     int acc = 0, rejected = 0;
     double pp = pri0, dd = dua0;
     for (int pass = 0; pass < s.polish_passes; ++pass) {
+      ex.tag(9);
       if (pass > 0) {
         ex.stages(NS, [&](int k) { save_stage(w, k, io.scratch); });
         ex.single([&]() { for (int r = 0; r < 4; ++r) io.scratch[30 * NS + r] = w.hdr()[H_YI + r]; });
@@ -118,13 +119,15 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
       if (pass > 0 && !changed) { settled = true; break; }
       ex.stages(NS, [&](int k) { polish_zero_stage(w, k); });
       ex.stages(NS, [&](int k) { assemble_stage(w, p, pm, k); });
-      ex.factor(w); ++n_fac;
+      ex.tag(10); ex.factor(w); ++n_fac;
+      ex.tag(11);
       for (int step = 0; step <= s.polish_refine_iter; ++step) {
         ex.stages(NS, [&](int k) { polish_rhs_fast(w, p, pc, k); });
         ex.solve(w); ++n_solve;
         ex.stages(NS, [&](int k) { polish_dual_fast(w, p, pc, k); });
         ex.stages(NS, [&](int k) { polish_primal_stage(w, k); });
       }
+      ex.tag(12);
       Residuals rp = compute_residuals(ex, w, p, s, ic, 1);
       bool ok;
       if (pass == 0) {
@@ -145,10 +148,11 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
   };
   auto resume_admm = [&]() {               // the polish replaced the factor and (maybe) the state
     n_pol = 0;
+    ex.tag(13);
     ex.stages(NS, [&](int k) { load_stage(w, k, io.warm); });
     ex.single([&]() { for (int r = 0; r < 4; ++r) w.hdr()[H_YI + r] = io.warm[30 * NS + r]; });
     ex.stages(NS, [&](int k) { assemble_stage(w, p, mode, k); });
-    ex.factor(w); ++n_fac;
+    ex.tag(14); ex.factor(w); ++n_fac;
   };
 
   // NOTE: every multi-statement lambda above has exactly ONE call site below, so that it is inlined and the solver
@@ -174,10 +178,12 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
         }
         bool attempt = converged || (last && status == STATUS_SOLVED);
         if (!attempt && !last && s.early_polish && can_polish) {
+          ex.tag(15);
           const int changed = ex.any(NS, [&](int k) { return activity_probe_stage(w, p, k); });
           attempt = (!changed || s.early_polish >= 2) && it >= s.early_polish_start;
         }
         if (attempt || last) {
+          ex.tag(8);
           if (io.warm) save_iterate();
           if (attempt && can_polish) {
             const bool clean = polish(res.pri, res.dua);

@@ -9,7 +9,10 @@ N, B = int(sys.argv[1]), int(sys.argv[2]); eps = float(sys.argv[3]) if len(sys.a
 par = MPCConfig(horizon=N).to_parameters(0.8)
 if N == 50: par = dataclasses.replace(par, du_bounds=((-12., 12.), (-0.02, 0.02)))
 x0, ref, up = make_batch(B, N, seed=3 if N == 50 else 2)
-ctl = MPCController(par, SolverSettings(eps_abs=eps, eps_rel=eps, polish_passes=5, polish_retry=2, early_polish=bool(int(os.environ.get('EARLY','1')))), max_batch=B)
+kw = dict(eps_abs=eps, eps_rel=eps, polish_passes=5, polish_retry=2, early_polish=bool(int(os.environ.get('EARLY','1'))))
+for k, v in os.environ.items():     # SET_<FIELD>=value overrides a SolverSettings field
+    if k.startswith("SET_"): kw[k[4:].lower()] = type(getattr(SolverSettings(), k[4:].lower()))(float(v))
+ctl = MPCController(par, SolverSettings(**kw), max_batch=B)
 d = lambda a: torch.as_tensor(a).cuda()
 dx0, dref, dup = d(x0), d(ref), d(up)
 r = ctl.solve_batch(dx0, dref, u_prev=dup); torch.cuda.synchronize()
@@ -20,5 +23,5 @@ for _ in range(3):
     best = min(best, e0.elapsed_time(e1))
 it = r.iters.double().mean().item()
 cyc = best * 1e-3 / (B * it) * 148 * 1.8e9
-print(f"[group] N={N} B={B} per_sm={ctl.problems_per_sm()}: {best:.2f} ms -> {B/best*1e3:.0f} solves/s, mean iters {it:.1f}, "
+print(f"[{" ".join(k[4:].lower()+"="+v for k,v in os.environ.items() if k.startswith("SET_")) or "default"}] N={N} B={B} per_sm={ctl.problems_per_sm()}: {best:.2f} ms -> {B/best*1e3:.0f} solves/s, mean iters {it:.1f}, "
       f"{cyc:.0f} SM-cycles per problem-iteration, solved {(r.status==1).sum().item()}")
