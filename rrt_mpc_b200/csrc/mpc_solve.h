@@ -68,11 +68,12 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
     ex.stages(NS, [&](int k) { cold_start_stage(w, p, k); });
   }
 
+  // The ADMM matrix is (re)assembled and factorised at ONE place, the top of the iteration loop, whenever need_factor
+  // is set (start, rho update, resume after a rejected polish); likewise the right-hand side phase.  One copy of that
+  // code instead of four keeps the kernel's hot instruction footprint small.
   Mode mode = admm_mode(rho, s);
-  ex.stages(NS, [&](int k) { assemble_stage(w, p, mode, k); });
-  ex.factor(w); ++n_fac;
   IterConst ic = iter_const(w, p, s, rho);
-  ex.stages(NS, [&](int k) { admm_rhs_fast(w, p, ic, k); });
+  bool need_factor = true;
 
   // ---- ADMM + polish --------------------------------------------------------------------------
   // OSQP: iterate until the residual test passes, then polish once.  Two opt-in extensions:
@@ -151,14 +152,21 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
     ex.tag(13);
     ex.stages(NS, [&](int k) { load_stage(w, k, io.warm); });
     ex.single([&]() { for (int r = 0; r < 4; ++r) w.hdr()[H_YI + r] = io.warm[30 * NS + r]; });
-    ex.stages(NS, [&](int k) { assemble_stage(w, p, mode, k); });
-    ex.tag(14); ex.factor(w); ++n_fac;
+    need_factor = true;
   };
 
   // NOTE: every multi-statement lambda above has exactly ONE call site below, so that it is inlined and the solver
   // state it captures stays in registers (a second call site makes nvcc outline it and spill the captures to local memory).
   bool finished = false, need_restore = false;
   while (!finished) {
+    if (need_factor) {
+      mode = admm_mode(rho, s);
+      ex.tag(4); ex.stages(NS, [&](int k) { assemble_stage(w, p, mode, k); });
+      ex.tag(5); ex.factor(w); ++n_fac;
+      ic = iter_const(w, p, s, rho);
+      need_factor = false;
+    }
+    ex.tag(6); ex.stages(NS, [&](int k) { admm_rhs_fast(w, p, ic, k); });
     ++it;
     ex.tag(1); ex.solve_iter(w); ++n_solve;
     ex.tag(2); ex.stages(NS, [&](int k) { admm_update_fast(w, p, ic, k); });
@@ -207,14 +215,10 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
         if (rho_new > rho * s.adaptive_rho_tolerance || rho_new < rho / s.adaptive_rho_tolerance) {
           ex.stages(NS, [&](int k) { rescale_v_stage(w, p, rho, rho_new, k); });
           rho = rho_new; ++n_rho;
-          mode = admm_mode(rho, s);
-          ex.tag(4); ex.stages(NS, [&](int k) { assemble_stage(w, p, mode, k); });
-          ex.tag(5); ex.factor(w); ++n_fac;
-          ic = iter_const(w, p, s, rho);
+          need_factor = true;
         }
       }
     }
-    if (!finished) { ex.tag(6); ex.stages(NS, [&](int k) { admm_rhs_fast(w, p, ic, k); }); }
   }
   ex.tag(7);
   if (need_restore) restore_iterate(io.warm);   // polish rejected outright: the answer is the ADMM iterate
