@@ -923,15 +923,17 @@ MPC_HD double* bx_ptr(const View& w, int k, int& rev) {
   if (k <= m) { rev = 0; return w.top().bx(k); }
   rev = 1; return w.bottom().bx(w.N - k);
 }
+// branch-free: entry j sits at p[j * st] with (p, st) = (row start, +1) in the top half, (row end, -1) in the bottom half,
+// so lanes on both sides of the middle stage stay converged
 MPC_HD void bx_load6(const View& w, int k, double* x) {
-  int rev; const double* b = bx_ptr(w, k, rev);
-  if (!rev) {
+  const int m = mid_stage(w.N);
+  const bool rev = k > m;
+  const double* top = w.top().bx(k);
+  const double* bot = w.bottom().bx(w.N - k) + 5;
+  const double* p = rev ? bot : top;
+  const int st = rev ? -1 : 1;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) x[j] = b[j];
-  } else {
-#pragma unroll
-    for (int j = 0; j < 6; ++j) x[j] = b[5 - j];
-  }
+  for (int j = 0; j < 6; ++j) x[j] = p[j * st];
 }
 
 // A1: consume x-tilde / s-tilde, relax x and s, update the row states
