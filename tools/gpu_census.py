@@ -9,7 +9,7 @@ N, B = int(sys.argv[1]), int(sys.argv[2]); early = bool(int(sys.argv[3])) if len
 par = MPCConfig(horizon=N).to_parameters(0.8)
 if N == 50: par = dataclasses.replace(par, du_bounds=((-12., 12.), (-0.02, 0.02)))
 x0, ref, up = make_batch(B, N, seed=3 if N == 50 else 2)
-kw = dict(eps_abs=1e-6, eps_rel=1e-6, polish_passes=5, polish_retry=2, early_polish=early)
+kw = dict(eps_abs=1e-6, eps_rel=1e-6, polish_passes=5, polish_retry=2, early_polish=int(sys.argv[3]) if len(sys.argv) > 3 else 1)
 for k, v in os.environ.items():
     if k.startswith("SET_"): kw[k[4:].lower()] = type(getattr(SolverSettings(), k[4:].lower()))(float(v))
 ctl = MPCController(par, SolverSettings(**kw), max_batch=B)
