@@ -707,9 +707,11 @@ MPC_HD void chain_cross_bwd(const double* lc, const double* nb, double* a) {
                           chain_load_cross(h.blk((k) - 1), h.bx((k) - 2), r0.lc, r0.nb); chain_store(h.bx(k), out); }
 
 // Forward sweep of one half over its local stages 0..H-2; returns the accumulators of the border stage in a[].
-// PIPE = true: software-pipelined by hand (two register sets, loop unrolled by two): the loads of stage k+1 are
-// issued BEFORE the arithmetic and the stores of stage k (the compiler cannot do this itself because it must
-// assume the stores alias the next loads); ~190 registers.  PIPE = false: one register set (~80 registers).
+//   PIPE = 0: one register set (~80 registers), the factor block of a stage is loaded at the top of the stage;
+//   PIPE = 1: software-pipelined by hand with two register sets, loop unrolled by two (needs > 255 registers: kept for the
+//             microbenchmark only);
+//   PIPE = 2: rolling refill (above), loop unrolled by two so that half of the refills have their consumer in the same
+//             loop body and ptxas interleaves them with the arithmetic (~165 registers).  Used by the ADMM loop.
 template <int PIPE>
 MPC_HD void half_forward(const HalfView& h, double* a) {
   const int last = h.H - 2;                 // last eliminated local stage

@@ -8,6 +8,7 @@ namespace mpc {
 
 // One lane sweeps one half of one problem: `bottom` selects the half, `partner` is the lane that holds the other
 // half of the same problem.  Called by ALL 32 lanes of the warp (inactive lanes only take part in the shuffles).
+// PIPE selects the sweep variant of mpc_core.h: 0 plain, 1 two register sets, 2 rolling refill.
 template <int PIPE>
 __device__ __forceinline__ void chain_twisted_lanes(bool active, bool bottom, int partner, const View& w) {
   double a[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, o[6], xm[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
