@@ -33,7 +33,7 @@ SEED = 3
 DU_DELTA = 0.02            # rad/step, configs[2] "tight steering-rate limits"
 EPS = 1e-6                 # parity setting of BASELINE.json (u0 within 1e-5 at eps_abs = eps_rel = 1e-6)
 POLISH_PASSES = 5
-POLISH_RETRY = 2
+POLISH_RETRY = 4           # with 4, every problem of the bench batch ends on a polished KKT point (2 leaves 1 of 65,536)
 EARLY_POLISH = 1          # finish as soon as a polish certifies a KKT point of a settled active set
 
 # canonical flop model of BASELINE.md §2 / SURVEY.md §8d (n = 11N+5, m = 19N+7, nnz(A) = 43N+5)

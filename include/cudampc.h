@@ -36,7 +36,7 @@ enum {
   CUDAMPC_OK = 0,
   CUDAMPC_ERR_INVALID = -1,     /* bad argument (NULL pointer, batch > max_batch, horizon out of range ...) */
   CUDAMPC_ERR_CUDA = -2,        /* a CUDA runtime call failed; see cudampc_last_error */
-  CUDAMPC_ERR_UNSUPPORTED = -3, /* e.g. non-diagonal Q/R/Q_N (this build keeps P diagonal) */
+  CUDAMPC_ERR_UNSUPPORTED = -3, /* e.g. a horizon whose workspace exceeds 227 KB of shared memory */
   CUDAMPC_ERR_NOMEM = -4
 };
 
@@ -123,6 +123,11 @@ int cudampc_set_params(cudampc_handle* h, const cudampc_params* params);
 int cudampc_linearize_batch(cudampc_handle* h, int batch, const double* ref_dev, double* A_dev, double* B_dev,
                             double* c_dev, void* stream);
 
+/* x_{k+1} = f_discrete(x_k, u_k) (vehicle_model.py:11-21), the integrator of the closed loop, as a parity hook.
+ *   x (B,4), u (B,2) -> out (B,4); dt_L (B,2) per-sample (dt, wheelbase_px) or NULL = the handle's parameters. */
+int cudampc_f_discrete_batch(cudampc_handle* h, int batch, const double* x_dev, const double* u_dev, const double* dt_L_dev,
+                             double* out_dev, void* stream);
+
 /* Solve `batch` independent tracking QPs.  Device pointers.
  *   in : x0 (B,4); ref (B,N+1,4) time-major [x,y,yaw,v]; u_prev (B,2) or NULL (= 0)
  *   out: u0 (B,2); Xp (B,4,N+1) state-major; Up (B,2,N); status (B) int32; iters (B) int32;
@@ -142,7 +147,8 @@ int cudampc_solve_batch_host(cudampc_handle* h, int batch, const double* x0, con
 
 /* build_reference for `batch` polylines (the input producer of the tracker).  Device pointers.
  *   in : paths (B, max_pts, 2) with n_pts[b] valid points each; desired_speed = MPCConfig.v_px_s; dt and horizon from params
- *   out: ref (B, ref_stride, 4) rows [x, y, unwrapped yaw, v_ref]; ref_len[b] = rows written, >= horizon+1 (tail padded);
+ *   out: ref (B, ref_stride, 4) rows [x, y, unwrapped yaw, v_ref]; ref_len[b] = rows written, >= horizon+1 (tail padded),
+ *        0 for an empty polyline (n_pts[b] < 1);
  *        a path that would need more than ref_stride rows is truncated to ref_stride (ref_len[b] == ref_stride). */
 int cudampc_build_reference_batch(cudampc_handle* h, int batch, const double* paths_dev, const int32_t* n_pts_dev, int max_pts,
                                   double desired_speed, double* ref_dev, int32_t* ref_len_dev, int ref_stride, void* stream);
@@ -150,11 +156,12 @@ int cudampc_build_reference_batch(cudampc_handle* h, int batch, const double* pa
 /* Closed-loop tracking of `batch` vehicles for cfg->sim_steps steps without host round trips
  * (TrajectoryTracker.track semantics per vehicle: window gather with tail padding, solve (+relaxation),
  * f_discrete, u_prev carry, path-index rule, goal mask).  Device pointers.
- *   in : ref_global (B, ref_stride, 4) with ref_len[b] valid rows each (>= 1; build_reference pads to N+1);
+ *   in : ref_global (B, ref_stride, 4) with ref_len[b] valid rows each (build_reference pads to N+1; a vehicle with
+ *        ref_len[b] < 1 takes no step and is flagged aborted, where control_stage.py:71-72 raises for an empty path);
  *        state0 (B,4); goal (B,2)
  *   out: states (B, sim_steps, 4) post-step states (rows after a vehicle stops are NaN);
  *        controls (B, sim_steps, 2) or NULL; n_steps (B) int32 = len(TrackingResult.states);
- *        flags (B) int32: bit0 goal reached, bit1 aborted on solver failure;
+ *        flags (B) int32: bit0 goal reached, bit1 aborted on solver failure, bit2 the relaxation retry ran at least once;
  *        step_status (B, sim_steps) int32 or NULL; step_iters (B, sim_steps) int32 or NULL. */
 int cudampc_rollout_batch(cudampc_handle* h, int batch, const double* ref_global_dev, const int32_t* ref_len_dev,
                           int ref_stride, const double* state0_dev, const double* goal_dev,

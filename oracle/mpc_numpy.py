@@ -63,7 +63,7 @@ class Settings:
     rho: float = 0.1
     alpha: float = 1.6
     sigma: float = 1e-6
-    scaling: int = 10               # Ruiz passes; <0 selects the "typewise" scaling of the CUDA path
+    scaling: int = 10               # Ruiz passes (OSQP default); 0 = unscaled, the CUDA path's mode
     check_termination: int = 25
     adaptive_rho_interval: int = 50  # fixed (upstream 0.6.x derives it from wall-clock time)
     adaptive_rho_tolerance: float = 5.0
@@ -243,14 +243,6 @@ def ruiz_scaling(P, q, A, iters):
         ct = 1.0 / cn
         P = P * ct; q = q * ct; c *= ct
     return D, E, c
-
-
-def typewise_scaling(lay, p: Params, q):
-    """Problem-independent equilibration used by the CUDA path: one column scale per variable type,
-    one row scale per row type (so that it lives in __constant__ memory), plus OSQP's scalar cost
-    scaling computed per problem.  See DESIGN.md §scaling."""
-    from . import typewise  # local import to keep this module standalone
-    return typewise.scaling_vectors(lay, p, q)
 
 
 # --------------------------------------------------------------------------------------

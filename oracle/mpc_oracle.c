@@ -724,7 +724,7 @@ int oracle_qp_dense(const oracle_params* p, const double* x0, const double* ref,
 }
 
 /* TrajectoryTracker.track for one vehicle (control_stage.py:74-157); returns number of states written.
- * flags: bit0 goal reached, bit1 aborted.  ref_global (len,4) from build_reference. */
+ * flags: bit0 goal reached, bit1 aborted, bit2 the relaxation retry (control_stage.py:45-56) ran at least once.  ref_global (len,4) from build_reference. */
 int oracle_track(const oracle_params* p, const oracle_settings* s, const double* ref_global, int len, const double* state0,
                  const double* goal, int sim_steps, double* states, double* controls, int* step_status, int* step_iters, int* flags) {
   int N = p->horizon;
@@ -742,6 +742,7 @@ int oracle_track(const oracle_params* p, const oracle_settings* s, const double*
       pr.du_bounds[0] -= 5.0; pr.du_bounds[1] += 5.0; pr.du_bounds[2] -= 0.05; pr.du_bounds[3] += 0.05;
       for (int k = 0; k <= N; ++k) win[4 * k + 3] *= 0.6;
       st = oracle_solve(&pr, s, state, win, u_prev, u0, Xp, Up, &it, &pri, &dua, NULL);
+      *flags |= 4;                                       /* the relaxation retry ran at least once */
     }
     if (step_status) step_status[step] = st;
     if (step_iters) step_iters[step] = it;

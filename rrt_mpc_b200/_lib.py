@@ -35,7 +35,7 @@ class RolloutCfg(C.Structure):
 # every symbol include/cudampc.h declares (tests/test_abi.py checks the library exports all of them)
 SYMBOLS = (
     "cudampc_version", "cudampc_default_settings", "cudampc_default_rollout_cfg", "cudampc_create",
-    "cudampc_destroy", "cudampc_last_error", "cudampc_set_params", "cudampc_linearize_batch",
+    "cudampc_destroy", "cudampc_last_error", "cudampc_set_params", "cudampc_linearize_batch", "cudampc_f_discrete_batch",
     "cudampc_solve_batch", "cudampc_solve_batch_host", "cudampc_build_reference_batch", "cudampc_rollout_batch", "cudampc_workspace_doubles",
     "cudampc_problems_per_sm", "cudampc_launch_count", "cudampc_fp64_peak_tflops",
 )
@@ -68,6 +68,8 @@ def load() -> C.CDLL:
     lib.cudampc_set_params.restype = C.c_int
     lib.cudampc_linearize_batch.argtypes = [vp, C.c_int, dp, dp, dp, dp, vp]
     lib.cudampc_linearize_batch.restype = C.c_int
+    lib.cudampc_f_discrete_batch.argtypes = [vp, C.c_int, dp, dp, dp, dp, vp]
+    lib.cudampc_f_discrete_batch.restype = C.c_int
     solve_args = [vp, C.c_int, dp, dp, dp, C.POINTER(Settings), dp, dp, dp, ip, ip, dp, dp, ip, vp]
     lib.cudampc_solve_batch.argtypes = solve_args
     lib.cudampc_solve_batch.restype = C.c_int

@@ -45,6 +45,7 @@ class BatchTrackingResult:
     aborted: np.ndarray       # (B,) bool   (solver failed even after the relaxation retry)
     step_status: np.ndarray   # (B, T) int32 OSQP codes (0 = not run)
     step_iters: np.ndarray    # (B, T) int32
+    relaxed: Optional[np.ndarray] = None   # (B,) bool: the relaxation retry (control_stage.py:45-56) ran at least once
 
     def result(self, b: int) -> TrackingResult:
         return TrackingResult(states=[self.states[b, t].copy() for t in range(int(self.n_steps[b]))])
@@ -52,12 +53,14 @@ class BatchTrackingResult:
     def save_npz(self, path: str) -> None:
         """Telemetry export (the reference keeps only the post-step states, artifacts.py:34-38): every array of the roll-out."""
         np.savez_compressed(path, states=self.states, controls=self.controls, n_steps=self.n_steps, goal_reached=self.goal_reached,
-                            aborted=self.aborted, step_status=self.step_status, step_iters=self.step_iters)
+                            aborted=self.aborted, step_status=self.step_status, step_iters=self.step_iters,
+                            relaxed=self.relaxed if self.relaxed is not None else np.zeros(len(self.n_steps), bool))
 
     @staticmethod
     def load_npz(path: str) -> "BatchTrackingResult":
         d = np.load(path)
-        return BatchTrackingResult(**{k: d[k] for k in ("states", "controls", "n_steps", "goal_reached", "aborted", "step_status", "step_iters")})
+        keys = ("states", "controls", "n_steps", "goal_reached", "aborted", "step_status", "step_iters", "relaxed")
+        return BatchTrackingResult(**{k: d[k] for k in keys if k in d.files})
 
 
 def initial_state(path, start) -> np.ndarray:
@@ -162,8 +165,12 @@ class TrajectoryTracker:
             stride = int(d_ref.shape[1])
         else:
             if ref_globals is None:
+                if any(len(p) < 1 for p in paths):
+                    raise RuntimeError("Planner returned an empty path")   # control_stage.py:71-72
                 ref_globals = [build_reference(p, self.mpc.v_px_s, N, self.mpc.dt) for p in paths]
             B = len(ref_globals)
+            if any(len(r) < 1 for r in ref_globals):
+                raise RuntimeError("Planner returned an empty path")
             lens = np.array([len(r) for r in ref_globals], dtype=np.int32)
             stride = int(lens.max())
             refg = np.zeros((B, stride, 4))
@@ -195,7 +202,7 @@ class TrajectoryTracker:
         flags = d_fl.cpu().numpy()
         return BatchTrackingResult(states=d_states.cpu().numpy(), controls=d_ctrl.cpu().numpy(), n_steps=d_n.cpu().numpy(),
                                    goal_reached=(flags & 1).astype(bool), aborted=(flags & 2).astype(bool),
-                                   step_status=d_st.cpu().numpy(), step_iters=d_it.cpu().numpy())
+                                   step_status=d_st.cpu().numpy(), step_iters=d_it.cpu().numpy(), relaxed=(flags & 4).astype(bool))
 
 
 def _reference_plotter():

@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 #include <new>
 
 #include "../../include/cudampc.h"
@@ -93,6 +94,22 @@ __global__ void mpc_linearize_kernel(Params p, int batch, const double* ref, dou
 }
 
 // ------------------------------------------------------------------------------------------------
+// K_f: batched f_discrete hook (parity at 1e-12 against vehicle_model.f_discrete, vehicle_model.py:11-21); the very
+// function the closed loop integrates with.  dt_L: optional per-sample (dt, wheelbase_px) pairs, else the handle's.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void f_discrete_dev(const Params& p, const double* x, const double* u, double* out);
+__global__ void mpc_f_discrete_kernel(Params p, int batch, const double* x, const double* u, const double* dt_L, double* out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  Params q = p;
+  if (dt_L) { q.dt = dt_L[2 * (size_t)b]; q.L = dt_L[2 * (size_t)b + 1]; }
+  double o[4];
+  f_discrete_dev(q, x + 4 * (size_t)b, u + 2 * (size_t)b, o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[4 * (size_t)b + i] = o[i];
+}
+
+// ------------------------------------------------------------------------------------------------
 // K_rollout: TrajectoryTracker.track for a batch of vehicles, all steps on the device
 // ------------------------------------------------------------------------------------------------
 struct RolloutArgs {
@@ -123,6 +140,15 @@ __device__ __forceinline__ void rollout_vehicle(Exec& ex, const View& w, const P
   double* wkb = a.work + (size_t)wk * b;     // [0..3] state, [4..5] u_prev, [6..7] u0, [10..11] status/iters (int), 16.. Xp, Up
   const double* refg = a.ref_global + (size_t)4 * a.ref_stride * b;
   const int len = a.ref_len[b];
+  if (len < 1) {                                           // control_stage.py:71-72 raises for an empty path; per vehicle: aborted, no steps
+    const int T0 = cfg.sim_steps;
+    ex.stages(T0 * 4, [&](int i) { a.states[(size_t)T0 * b * 4 + i] = nan_; });
+    if (a.controls) ex.stages(T0 * 2, [&](int i) { a.controls[(size_t)T0 * b * 2 + i] = nan_; });
+    if (a.step_status) ex.stages(T0, [&](int i) { a.step_status[(size_t)T0 * b + i] = 0; });
+    if (a.step_iters) ex.stages(T0, [&](int i) { a.step_iters[(size_t)T0 * b + i] = 0; });
+    ex.single([&]() { a.n_steps[b] = 0; a.flags[b] = 2; });
+    return;
+  }
   ex.single([&]() {
     for (int i = 0; i < 4; ++i) wkb[i] = a.state0[4 * (size_t)b + i];
     wkb[4] = 0.0; wkb[5] = 0.0;
@@ -152,6 +178,7 @@ __device__ __forceinline__ void rollout_vehicle(Exec& ex, const View& w, const P
       solve_problem(ex, w, pr, ss, io);
       ex.group_sync();
       status = *st_out;
+      flags |= 4;
     }
     if (status != STATUS_SOLVED && status != STATUS_SOLVED_INACCURATE) { flags |= 2; break; }
     // integrate, carry u_prev, path index rule, goal test (control_stage.py:127-150)
@@ -209,6 +236,7 @@ __global__ void mpc_build_reference_kernel(int batch, const double* paths, const
   const double* P = paths + (size_t)2 * max_pts * b;
   double* R = ref + (size_t)4 * stride * b;
   const int n = n_pts[b];
+  if (n < 1) { ref_len[b] = 0; return; }                   // empty polyline: no reference (the tracker flags such a vehicle as aborted)
   const double step = fmax(2.0, 0.8 * v * dt);
   // total arc length (sequential cumsum, as np.cumsum)
   double total = 0.0;
@@ -297,6 +325,17 @@ struct cudampc_handle {
 
 static char g_create_err[512] = "";
 
+// Every entry point runs on the handle's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+  int prev = -1; bool switched = false; cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) { err = cudaSetDevice(dev); switched = (err == cudaSuccess); }
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(h) DeviceGuard guard_((h)->device); CU(h, guard_.err)
+
 static int fail(cudampc_handle* h, int code, const char* fmt, const char* detail) {
   char* dst = h ? h->err : g_create_err;
   snprintf(dst, 512, fmt, detail ? detail : "");
@@ -312,24 +351,50 @@ static int fail(cudampc_handle* h, int code, const char* fmt, const char* detail
     }                                                                                       \
   } while (0)
 
-static bool is_diag(const double* m, int n) {
-  for (int i = 0; i < n; ++i)
-    for (int j = 0; j < n; ++j)
-      if (i != j && m[i * n + j] != 0.0) return false;
-  return true;
+// Smallest eigenvalue of the symmetric n x n matrix W (n <= 4), cyclic Jacobi.  cp.quad_form (mpc_controller.py:74-75,112)
+// accepts any PSD matrix; the library accepts exactly those (relative tolerance 1e-12) and rejects indefinite ones.
+static double min_eig_sym(const double* Win, int n, double* scale) {
+  double a[4][4];
+  double mx = 0.0;
+  for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) { a[i][j] = Win[i * n + j]; if (fabs(a[i][j]) > mx) mx = fabs(a[i][j]); }
+  *scale = mx;
+  for (int sweep = 0; sweep < 50; ++sweep) {
+    double off = 0.0;
+    for (int i = 0; i < n; ++i) for (int j = 0; j < i; ++j) off += a[i][j] * a[i][j];
+    if (off <= 1e-30 * mx * mx) break;
+    for (int p = 0; p < n; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        if (a[p][q] == 0.0) continue;
+        const double th = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+        const double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0)), c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < n; ++k) { const double x = a[k][p], y = a[k][q]; a[k][p] = c * x - sn * y; a[k][q] = sn * x + c * y; }
+        for (int k = 0; k < n; ++k) { const double x = a[p][k], y = a[q][k]; a[p][k] = c * x - sn * y; a[q][k] = sn * x + c * y; }
+      }
+  }
+  double mn = a[0][0];
+  for (int i = 1; i < n; ++i) if (a[i][i] < mn) mn = a[i][i];
+  return mn;
 }
 
 static int convert_params(const cudampc_params* in, Params* p, cudampc_handle* h) {
   if (!in) return fail(h, CUDAMPC_ERR_INVALID, "%s", "params is NULL");
   if (in->horizon < 1 || in->horizon > 256) return fail(h, CUDAMPC_ERR_INVALID, "%s", "horizon must be in [1, 256]");
   if (!(in->dt > 0.0) || !(in->wheelbase_px > 0.0)) return fail(h, CUDAMPC_ERR_INVALID, "%s", "dt and wheelbase_px must be > 0");
-  if (!is_diag(in->q, 4) || !is_diag(in->r, 2) || !is_diag(in->q_terminal, 4))
-    return fail(h, CUDAMPC_ERR_UNSUPPORTED, "%s", "non-diagonal q / r / q_terminal are not supported by this build");
   p->L = in->wheelbase_px; p->dt = in->dt; p->N = in->horizon;
-  for (int i = 0; i < 4; ++i) { p->q[i] = in->q[5 * i]; p->qn[i] = in->q_terminal[5 * i]; }
-  for (int i = 0; i < 2; ++i) p->r[i] = in->r[3 * i];
-  for (int i = 0; i < 4; ++i) if (!(p->q[i] > 0.0) || !(p->qn[i] > 0.0)) return fail(h, CUDAMPC_ERR_INVALID, "%s", "q and q_terminal diagonals must be > 0");
-  for (int i = 0; i < 2; ++i) if (!(p->r[i] > 0.0)) return fail(h, CUDAMPC_ERR_INVALID, "%s", "r diagonal must be > 0");
+  // quad_form(e, W) = e'We = 1/2 e'(W + W')e: the P block of the QP is the symmetric matrix W + W'
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) { p->pq[i][j] = in->q[4 * i + j] + in->q[4 * j + i]; p->pqn[i][j] = in->q_terminal[4 * i + j] + in->q_terminal[4 * j + i]; }
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j) p->pr[i][j] = in->r[2 * i + j] + in->r[2 * j + i];
+  {
+    double sc;
+    double e = min_eig_sym(&p->pq[0][0], 4, &sc);
+    if (!(sc > 0.0) || !(e >= -1e-12 * sc) || !isfinite(e)) return fail(h, CUDAMPC_ERR_INVALID, "%s", "q must be positive semidefinite and non-zero");
+    e = min_eig_sym(&p->pqn[0][0], 4, &sc);
+    if (!(sc > 0.0) || !(e >= -1e-12 * sc) || !isfinite(e)) return fail(h, CUDAMPC_ERR_INVALID, "%s", "q_terminal must be positive semidefinite and non-zero");
+    e = min_eig_sym(&p->pr[0][0], 2, &sc);
+    if (!(sc > 0.0) || !(e >= -1e-12 * sc) || !isfinite(e)) return fail(h, CUDAMPC_ERR_INVALID, "%s", "r must be positive semidefinite and non-zero");
+  }
   p->u_lo[0] = in->u_bounds[0]; p->u_hi[0] = in->u_bounds[1]; p->u_lo[1] = in->u_bounds[2]; p->u_hi[1] = in->u_bounds[3];
   p->v_lo = in->v_bounds[0]; p->v_hi = in->v_bounds[1];
   p->du_lo[0] = in->du_bounds[0]; p->du_hi[0] = in->du_bounds[1]; p->du_lo[1] = in->du_bounds[2]; p->du_hi[1] = in->du_bounds[3];
@@ -344,11 +409,17 @@ static int convert_settings(const cudampc_settings* in, Settings* s, cudampc_han
   if (!(in->eps_abs >= 0.0) || !(in->eps_rel >= 0.0) || !(in->rho > 0.0) || !(in->alpha > 0.0 && in->alpha < 2.0) ||
       !(in->sigma > 0.0) || in->max_iter < 1 || !(in->delta > 0.0))
     return fail(h, CUDAMPC_ERR_INVALID, "%s", "settings out of range");
+  if (!(in->rho_min > 0.0) || !(in->rho_max >= in->rho_min) || !(in->rho_eq_factor > 0.0) || !(in->adaptive_rho_tolerance >= 1.0) ||
+      in->check_termination < 0 || in->adaptive_rho_interval < 0 || in->polish_passes < 0 || in->polish_refine_iter < 0)
+    return fail(h, CUDAMPC_ERR_INVALID, "%s", "settings out of range (rho_min > 0, rho_max >= rho_min, rho_eq_factor > 0, adaptive_rho_tolerance >= 1, intervals >= 0)");
   s->eps_abs = in->eps_abs; s->eps_rel = in->eps_rel; s->rho0 = in->rho; s->alpha = in->alpha; s->sigma = in->sigma;
   s->adaptive_rho_tolerance = in->adaptive_rho_tolerance; s->rho_eq_factor = in->rho_eq_factor;
   s->rho_min = in->rho_min; s->rho_max = in->rho_max; s->delta = in->delta;
   s->max_iter = in->max_iter; s->check_termination = in->check_termination; s->adaptive_rho = in->adaptive_rho;
-  s->adaptive_rho_interval = in->adaptive_rho_interval; s->polish_passes = in->polish_passes;
+  // OSQP's adaptive_rho_interval = 0 means "automatic" (wall-clock based upstream, hence non-deterministic); its documented
+  // fixed fallback is a multiple of check_termination.  Map 0 to 2 * check_termination (= this library's default of 50).
+  s->adaptive_rho_interval = in->adaptive_rho_interval > 0 ? in->adaptive_rho_interval : 2 * (in->check_termination > 0 ? in->check_termination : 25);
+  s->polish_passes = in->polish_passes;
   s->polish_refine_iter = in->polish_refine_iter; s->warm_start = in->warm_start;
   s->polish_retry = in->polish_retry < 0 ? 0 : in->polish_retry;
   s->early_polish = in->early_polish; s->early_polish_start = in->early_polish_start;
@@ -388,7 +459,8 @@ int cudampc_create(const cudampc_params* params, int max_batch, int device, cuda
   int ndev = 0;
   CU(nullptr, cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(nullptr, CUDAMPC_ERR_INVALID, "%s", "device index out of range");
-  CU(nullptr, cudaSetDevice(device));
+  DeviceGuard guard_(device);
+  CU(nullptr, guard_.err);
   cudampc_handle* h = new (std::nothrow) cudampc_handle();
   if (!h) return fail(nullptr, CUDAMPC_ERR_NOMEM, "%s", "host allocation failed");
   memset(h, 0, sizeof *h);
@@ -446,7 +518,7 @@ int cudampc_create(const cudampc_params* params, int max_batch, int device, cuda
 
 int cudampc_destroy(cudampc_handle* h) {
   if (!h) return CUDAMPC_OK;
-  cudaSetDevice(h->device);
+  DeviceGuard guard_(h->device);
   cudaFree(h->warm); cudaFree(h->scratch); cudaFree(h->work); cudaFree(h->counter);
   cudaFree(h->d_in); cudaFree(h->d_out);
   if (h->h_in) cudaFreeHost(h->h_in);
@@ -467,7 +539,8 @@ int cudampc_set_params(cudampc_handle* h, const cudampc_params* params) {
 
 double cudampc_fp64_peak_tflops(cudampc_handle* h) {
   if (!h) return -1.0;
-  if (cudaSetDevice(h->device) != cudaSuccess) return -1.0;
+  DeviceGuard guard_(h->device);
+  if (guard_.err != cudaSuccess) return -1.0;
   const int blocks = h->sms * 8, threads = 256, iters = 20000;
   double* out = nullptr;
   if (cudaMalloc(&out, sizeof(double) * blocks * threads) != cudaSuccess) return -1.0;
@@ -496,12 +569,24 @@ int cudampc_linearize_batch(cudampc_handle* h, int batch, const double* ref_dev,
   if (!h) return CUDAMPC_ERR_INVALID;
   if (batch < 0 || !ref_dev || !A_dev || !B_dev || !c_dev) return fail(h, CUDAMPC_ERR_INVALID, "%s", "linearize_batch: NULL pointer or negative batch");
   if (batch == 0) return CUDAMPC_OK;
-  CU(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   const int wpb = 4;
   int grid = (batch + wpb - 1) / wpb;
   if (grid > h->sms * 8) grid = h->sms * 8;
   size_t sm = (size_t)wpb * (h->N + 1) * sizeof(double);
   mpc_linearize_kernel<<<grid, 32 * wpb, sm, (cudaStream_t)stream>>>(h->p, batch, ref_dev, A_dev, B_dev, c_dev);
+  h->launches++;
+  CU(h, cudaGetLastError());
+  return CUDAMPC_OK;
+}
+
+int cudampc_f_discrete_batch(cudampc_handle* h, int batch, const double* x_dev, const double* u_dev, const double* dt_L_dev,
+                             double* out_dev, void* stream) {
+  if (!h) return CUDAMPC_ERR_INVALID;
+  if (batch < 0 || !x_dev || !u_dev || !out_dev) return fail(h, CUDAMPC_ERR_INVALID, "%s", "f_discrete_batch: NULL pointer or negative batch");
+  if (batch == 0) return CUDAMPC_OK;
+  ON_DEVICE(h);
+  mpc_f_discrete_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->p, batch, x_dev, u_dev, dt_L_dev, out_dev);
   h->launches++;
   CU(h, cudaGetLastError());
   return CUDAMPC_OK;
@@ -519,7 +604,7 @@ int cudampc_solve_batch(cudampc_handle* h, int batch, const double* x0_dev, cons
   int rc = convert_settings(settings, &s, h);
   if (rc) return rc;
   if (batch == 0) return CUDAMPC_OK;
-  CU(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   cudaStream_t st = (cudaStream_t)stream;
   CU(h, cudaMemsetAsync(h->counter, 0, sizeof(int), st));
   BatchArgs a;
@@ -550,7 +635,7 @@ int cudampc_solve_batch_host(cudampc_handle* h, int batch, const double* x0, con
   if (batch < 0 || batch > h->max_batch) return fail(h, CUDAMPC_ERR_INVALID, "%s", "solve_batch_host: batch out of range for this handle");
   if (!x0 || !ref || !u0 || !Xp || !Up || !status || !iters) return fail(h, CUDAMPC_ERR_INVALID, "%s", "solve_batch_host: NULL pointer");
   if (batch == 0) return CUDAMPC_OK;
-  CU(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   cudaStream_t st = (cudaStream_t)stream;
   const int N = h->N;
   const size_t B = (size_t)batch;
@@ -614,7 +699,7 @@ int cudampc_build_reference_batch(cudampc_handle* h, int batch, const double* pa
   if (batch < 0 || !paths_dev || !n_pts_dev || !ref_dev || !ref_len_dev || max_pts < 1 || ref_stride < h->N + 1 || !(desired_speed > 0.0))
     return fail(h, CUDAMPC_ERR_INVALID, "%s", "build_reference_batch: NULL pointer, max_pts < 1, ref_stride < horizon+1 or speed <= 0");
   if (batch == 0) return CUDAMPC_OK;
-  CU(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   mpc_build_reference_kernel<<<(batch + 63) / 64, 64, 0, (cudaStream_t)stream>>>(batch, paths_dev, n_pts_dev, max_pts, desired_speed, h->p.dt,
                                                                                  h->N, ref_dev, ref_len_dev, ref_stride);
   h->launches++;
@@ -638,7 +723,7 @@ int cudampc_rollout_batch(cudampc_handle* h, int batch, const double* ref_global
   int rc = convert_settings(settings, &s, h);
   if (rc) return rc;
   if (batch == 0) return CUDAMPC_OK;
-  CU(h, cudaSetDevice(h->device));
+  ON_DEVICE(h);
   cudaStream_t st = (cudaStream_t)stream;
   CU(h, cudaMemsetAsync(h->counter, 0, sizeof(int), st));
   RolloutArgs a;

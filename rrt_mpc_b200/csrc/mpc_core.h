@@ -34,7 +34,8 @@ namespace mpc {
 // ----------------------------------------------------------------------------------------------
 struct Params {
   double L, dt;
-  double q[4], r[2], qn[4];          // diagonals of Q, R, Q_N (objective uses 2*these as P)
+  double pq[4][4], pr[2][2], pqn[4][4];   // P blocks of the objective: Q + Q', R + R', Q_N + Q_N' (symmetric; cp.quad_form
+                                          // accepts any PSD matrix, mpc_controller.py:74-75,112)
   double u_lo[2], u_hi[2];
   double v_lo, v_hi;
   double du_lo[2], du_hi[2];
@@ -298,6 +299,15 @@ MPC_HD double group_g(int k, int g, const XV& xv) {
   return k > 0 ? cur - xv(k - 1, 4 + g - 3) : cur;
 }
 
+// (P x)_j for the six (x,u) unknowns of a stage; W = pq or pqn
+MPC_HD double px_entry(const Params& p, bool reg, int j, const double* x) {
+  if (j < 4) {
+    const double (*W)[4] = reg ? p.pq : p.pqn;
+    return W[j][0] * x[0] + W[j][1] * x[1] + W[j][2] * x[2] + W[j][3] * x[3];
+  }
+  return p.pr[j - 4][0] * x[4] + p.pr[j - 4][1] * x[5];
+}
+
 struct StateXV { View w; MPC_HD double operator()(int k, int j) const { return w.rec(k)[R_XU + j]; } };
 struct BxXV { View w; MPC_HD double operator()(int k, int j) const { return w.bx_get(k, j); } };
 
@@ -340,12 +350,10 @@ MPC_HD void setup_stage(const View& w, const Params& p, int k, const RefWin& rw,
   } else {
     for (int j = 0; j < 7; ++j) rc[R_LIN + j] = 0.0;
   }
-  const double* qd = k < N ? p.q : p.qn;
+  const double (*W)[4] = k < N ? p.pq : p.pqn;
   const double* r = rw.row(k);
-  rc[R_Q + 0] = -2.0 * qd[0] * r[0];
-  rc[R_Q + 1] = -2.0 * qd[1] * r[1];
-  rc[R_Q + 2] = -2.0 * qd[2] * uyaw[k];
-  rc[R_Q + 3] = -2.0 * qd[3] * rw.v(k);
+  const double xr[4] = {r[0], r[1], uyaw[k], rw.v(k)};
+  for (int i = 0; i < 4; ++i) rc[R_Q + i] = -(W[i][0] * xr[0] + W[i][1] * xr[1] + W[i][2] * xr[2] + W[i][3] * xr[3]);
 }
 
 // cold start: x = 0, y = 0, z = clip(0, l, u)  (v = z for inequality rows)
@@ -394,9 +402,12 @@ MPC_HD void stage_cross(const View& w, const Params& p, const Mode& m, int k, do
 MPC_HD void stage_diag(const View& w, const Params& p, const Mode& m, int k, double D[6][6]) {
   const int N = w.N;
   for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) D[a][b] = 0.0;
-  const double* qd = k < N ? p.q : p.qn;
-  for (int j = 0; j < 4; ++j) D[j][j] = 2.0 * qd[j] + m.reg;
-  if (k < N) { D[4][4] = 2.0 * p.r[0] + m.reg; D[5][5] = 2.0 * p.r[1] + m.reg; }
+  const double (*W)[4] = k < N ? p.pq : p.pqn;
+  for (int a = 0; a < 4; ++a) {
+    for (int b = 0; b < a; ++b) D[a][b] = W[a][b];
+    D[a][a] = W[a][a] + m.reg;
+  }
+  if (k < N) { D[4][4] = p.pr[0][0] + m.reg; D[5][5] = p.pr[1][1] + m.reg; D[5][4] = p.pr[1][0]; }
   else { D[4][4] = 1.0; D[5][5] = 1.0; }
   // rows arriving at x_k: init rows (k == 0) or dynamics rows of stage k-1
   if (k == 0) {
@@ -1101,11 +1112,9 @@ MPC_HD void residual_stage(const View& w, const Params& p, double rho, int ymode
   }
   // dual
   double aty[6]; gather_xu(w, p, k, rp, aty);
-  const double* qd = k < N ? p.q : p.qn;
   const int nj = k < N ? 6 : 4;
   for (int j = 0; j < nj; ++j) {
-    double pd = j < 4 ? 2.0 * qd[j] : 2.0 * p.r[j - 4];
-    double px = pd * rc[R_XU + j];
+    double px = px_entry(p, k < N, j, rc + R_XU);
     double qj = j < 4 ? rc[R_Q + j] : 0.0;
     r[3] = dmax(r[3], fabs(px + qj + aty[j])); r[4] = dmax(r[4], fabs(px)); r[5] = dmax(r[5], fabs(aty[j]));
     r[6] = dmax(r[6], fabs(qj));
@@ -1259,12 +1268,10 @@ MPC_HD void polish_rhs_stage(const View& w, const Params& p, const Mode& m, int 
   }
   double out[6];
   gather_xu(w, p, k, rp, out);
-  const double* qd = k < N ? p.q : p.qn;
   const int nj = k < N ? 6 : 4;
   for (int j = 0; j < nj; ++j) {
-    double pd = j < 4 ? 2.0 * qd[j] : 2.0 * p.r[j - 4];
     double qj = j < 4 ? rc[R_Q + j] : 0.0;
-    w.bx_set(k, j, -qj - pd * rc[R_XU + j] + out[j]);
+    w.bx_set(k, j, -qj - px_entry(p, k < N, j, rc + R_XU) + out[j]);
   }
   for (int j = nj; j < 6; ++j) w.bx_set(k, j, 0.0);
 }
@@ -1433,15 +1440,11 @@ MPC_HD void polish_rhs_fast(const View& w, const Params& p, const PolConst& c, i
       }
     }
   }
-  const double* qd = reg ? p.q : p.qn;
   int rev; double* bp = bx_ptr(w, k, rev);
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
     double val = 0.0;
-    if (j < 4 || reg) {
-      const double pd = j < 4 ? 2.0 * qd[j < 4 ? j : 0] : 2.0 * p.r[j < 4 ? 0 : j - 4];
-      val = -(j < 4 ? rc[R_Q + j] : 0.0) - pd * x[j] + out[j];
-    }
+    if (j < 4 || reg) val = -(j < 4 ? rc[R_Q + j] : 0.0) - px_entry(p, reg, j, x) + out[j];
     bp[rev ? 5 - j : j] = val;
   }
   if (k == mid_stage(N)) {
@@ -1589,12 +1592,10 @@ MPC_HD void residual_fast(const View& w, const Params& p, const IterConst& c, in
       }
     }
   }
-  const double* qd = reg ? p.q : p.qn;
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
     if (j < 4 || reg) {
-      const double pd = j < 4 ? 2.0 * qd[j < 4 ? j : 0] : 2.0 * p.r[j < 4 ? 0 : j - 4];
-      const double px = pd * x[j], qj = j < 4 ? rc[R_Q + j] : 0.0;
+      const double px = px_entry(p, reg, j, x), qj = j < 4 ? rc[R_Q + j] : 0.0;
       r[3] = dmax(r[3], fabs(px + qj + aty[j])); r[4] = dmax(r[4], fabs(px)); r[5] = dmax(r[5], fabs(aty[j]));
       r[6] = dmax(r[6], fabs(qj));
     }

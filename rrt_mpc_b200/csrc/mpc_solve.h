@@ -60,10 +60,13 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
 
   // ---- initial iterate -------------------------------------------------------------------
   double rho = s.rho0;
-  if (s.warm_start && io.warm) {
+  // A slot is warm only if a previous solve left a usable iterate in it: the rho word doubles as the valid marker
+  // (cudampc_create zeroes the buffer; a solve that ended on non-finite residuals stores 0).  Anything else starts cold.
+  const double rho_slot = (s.warm_start && io.warm) ? io.warm[30 * NS + 4] : 0.0;
+  if (rho_slot >= s.rho_min && rho_slot <= s.rho_max) {
     ex.stages(NS, [&](int k) { load_stage(w, k, io.warm); });
     ex.single([&]() { for (int r = 0; r < 4; ++r) w.hdr()[H_YI + r] = io.warm[30 * NS + r]; });
-    rho = io.warm[30 * NS + 4];
+    rho = rho_slot;
   } else {
     ex.stages(NS, [&](int k) { cold_start_stage(w, p, k); });
   }
@@ -94,7 +97,7 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
     ex.stages(NS, [&](int k) { save_stage(w, k, io.warm); });
     ex.single([&]() {
       for (int r = 0; r < 4; ++r) io.warm[30 * NS + r] = w.hdr()[H_YI + r];
-      io.warm[30 * NS + 4] = rho;
+      io.warm[30 * NS + 4] = (res.pri < 1e300 && res.dua < 1e300) ? rho : 0.0;      // NaN / inf residuals: slot invalid
     });
   };
   auto restore_iterate = [&](const double* src) {

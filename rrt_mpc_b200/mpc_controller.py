@@ -255,8 +255,12 @@ class MPCController:
                           torch.empty((B, 4), dtype=torch.int32, device=dev))
         if B == 0:
             return out
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
         if self._h is None:
-            self._device = dev.index if dev.index is not None else torch.cuda.current_device()
+            self._device = idx
+        elif idx != self._h.device:
+            raise ValueError(f"tensors live on cuda:{idx} but this controller's handle was created on cuda:{self._h.device}; "
+                             "use one MPCController per device")
         h = self._handle(B)
         st = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
@@ -274,6 +278,8 @@ class MPCController:
         N = self._params.horizon
         B = len(paths)
         npts = np.array([len(p) for p in paths], dtype=np.int32)
+        if B and npts.min() < 1:
+            raise RuntimeError("Planner returned an empty path")          # control_stage.py:71-72
         max_pts = int(npts.max()) if B else 1
         buf = np.zeros((B, max_pts, 2))
         for b, p in enumerate(paths):
@@ -293,6 +299,25 @@ class MPCController:
                                                  stride, C.c_void_p(st))
         _lib.check(h.lib, h.ptr, rc, "cudampc_build_reference_batch")
         return ref, ref_len
+
+    def f_discrete_batch(self, x, u, dt_L=None):
+        """``f_discrete`` (vehicle_model.py:11-21) for ``x (B,4)``, ``u (B,2)`` on the device - the integrator of the closed
+        loop, exposed for parity checks.  ``dt_L (B,2)``: per-sample ``(dt, wheelbase_px)``; default: this controller's."""
+        import torch
+        dev = torch.device("cuda", self._device)
+        t = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+        dx, du = t(x).reshape(-1, 4), t(u).reshape(-1, 2)
+        B = dx.shape[0]
+        if du.shape[0] != B:
+            raise ValueError("x and u must have the same leading dimension")
+        dd = None if dt_L is None else t(dt_L).reshape(B, 2)
+        out = torch.empty((B, 4), dtype=torch.float64, device=dev)
+        h = self._handle(max(B, 1))
+        st = torch.cuda.current_stream(dev).cuda_stream
+        rc = h.lib.cudampc_f_discrete_batch(h.ptr, B, C.c_void_p(dx.data_ptr()), C.c_void_p(du.data_ptr()),
+                                            C.c_void_p(dd.data_ptr()) if dd is not None else None, C.c_void_p(out.data_ptr()), C.c_void_p(st))
+        _lib.check(h.lib, h.ptr, rc, "cudampc_f_discrete_batch")
+        return out.cpu().numpy()
 
     def linearize_batch(self, ref):
         """(A (B,N,4,4), B (B,N,4,2), c (B,N,4)) as ``solve`` linearises them (mpc_controller.py:59-70,108-109)."""

@@ -37,15 +37,15 @@ int emu_footprint(int N) { return footprint(N); }
 int emu_warm_size(int N) { return warm_size(N); }
 
 // params/settings passed as flat double arrays to keep the ctypes side trivial
-//  par: L, dt, q[4], r[2], qn[4], u_lo[2], u_hi[2], v_lo, v_hi, du_lo[2], du_hi[2], w_v, w_u, w_du   (25)
+//  par: L, dt, (Q+Q')[16], (R+R')[4], (QN+QN')[16], u_lo[2], u_hi[2], v_lo, v_hi, du_lo[2], du_hi[2], w_v, w_u, w_du   (51)
 //  set: eps_abs, eps_rel, rho0, alpha, sigma, adaptive_rho_tolerance, rho_eq_factor, rho_min, rho_max, delta,
 //       max_iter, check_termination, adaptive_rho, adaptive_rho_interval, polish_passes, polish_refine_iter, warm_start, polish_retry (18)
 static void unpack(const double* par, const double* set, int N, Params& p, Settings& s) {
   int i = 0;
   p.L = par[i++]; p.dt = par[i++];
-  for (int j = 0; j < 4; ++j) p.q[j] = par[i++];
-  for (int j = 0; j < 2; ++j) p.r[j] = par[i++];
-  for (int j = 0; j < 4; ++j) p.qn[j] = par[i++];
+  for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) p.pq[a][b] = par[i++];      // already symmetrised: Q + Q'
+  for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) p.pr[a][b] = par[i++];
+  for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) p.pqn[a][b] = par[i++];
   for (int j = 0; j < 2; ++j) p.u_lo[j] = par[i++];
   for (int j = 0; j < 2; ++j) p.u_hi[j] = par[i++];
   p.v_lo = par[i++]; p.v_hi = par[i++];

@@ -23,7 +23,8 @@ def _P(a):
 
 
 def pack(p, **s):
-    par = np.array([p.wheelbase_px, p.dt, *np.diag(p.q), *np.diag(p.r), *np.diag(p.q_terminal),
+    sym = lambda m: (np.asarray(m, float) + np.asarray(m, float).T).ravel()
+    par = np.array([p.wheelbase_px, p.dt, *sym(p.q), *sym(p.r), *sym(p.q_terminal),
                     p.u_bounds[0][0], p.u_bounds[1][0], p.u_bounds[0][1], p.u_bounds[1][1], p.v_bounds[0], p.v_bounds[1],
                     p.du_bounds[0][0], p.du_bounds[1][0], p.du_bounds[0][1], p.du_bounds[1][1],
                     p.slack_velocity, p.slack_input, p.slack_rate], float)

@@ -52,10 +52,10 @@ def test_create_rejects_bad_arguments_without_touching_the_device():
     p = params_to_c(product_params(20))
     assert lib.cudampc_create(C.byref(p), 0, 0, C.byref(h)) == -1                    # max_batch < 1
     assert b"max_batch" in lib.cudampc_last_error(None)
-    q = np.diag([4.0, 4.0, 0.6, 0.1]); q[0, 1] = q[1, 0] = 0.5
+    q = np.diag([4.0, 4.0, 0.6, 0.1]); q[0, 1] = q[1, 0] = 5.0                       # indefinite: cvxpy's quad_form would refuse it too
     p2 = params_to_c(dataclasses.replace(product_params(20), q=q))
-    assert lib.cudampc_create(C.byref(p2), 8, 0, C.byref(h)) == -3                   # non-diagonal Q: UNSUPPORTED, loud
-    assert b"non-diagonal" in lib.cudampc_last_error(None)
+    assert lib.cudampc_create(C.byref(p2), 8, 0, C.byref(h)) == -1
+    assert b"positive semidefinite" in lib.cudampc_last_error(None)
     p3 = params_to_c(dataclasses.replace(product_params(20), horizon=0))
     assert lib.cudampc_create(C.byref(p3), 8, 0, C.byref(h)) == -1
     assert lib.cudampc_solve_batch(None, 1, None, None, None, None, None, None, None, None, None, None, None, None, None) == -1

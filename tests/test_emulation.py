@@ -141,3 +141,34 @@ def test_warm_start_converges_faster_to_same_optimum():
     assert hot["iters"].sum() < 0.6 * ref["iters"].sum()
     assert np.abs(hot["u0"] - ref["u0"]).max() < 1e-7
     assert cold["iters"].sum() == E.solve(p, g["n20_x0"][:nb], g["n20_ref"][:nb], g["n20_up"][:nb], polish_passes=3, **TIGHT)["iters"].sum()
+
+
+def test_non_diagonal_weights_against_reference_outputs():
+    """cp.quad_form accepts any PSD Q / R / Q_N (mpc_controller.py:74-75,112); fixture nd20 of tests/golden/ref_qp.npz is
+    what the reference's own solve() returned for such weights."""
+    g = load_golden("ref_qp.npz")
+    p = dataclasses.replace(O.Params(horizon=20), q=g["nd20_q"], r=g["nd20_r"], q_terminal=g["nd20_qn"])
+    r = E.solve(p, g["nd20_x0"], g["nd20_ref"], g["nd20_up"], polish_passes=3, **TIGHT)
+    assert (r["status"] == 1).all()
+    assert np.abs(r["u0"] - g["nd20_u0"]).max() < 1e-8
+    assert np.abs(r["Xp"] - g["nd20_X"]).max() < 1e-7 and np.abs(r["Up"] - g["nd20_U"]).max() < 1e-7
+    c = CO.solve_batch(p, g["nd20_x0"], g["nd20_ref"], g["nd20_up"], scaling=0, z0_projected=1, **TIGHT)
+    assert np.array_equal(r["iters"], c["iters"]) and np.array_equal(r["status"], c["status"])
+
+
+def test_warm_start_from_a_never_solved_slot_starts_cold():
+    """A zeroed warm buffer (what cudampc_create allocates) must not be read as an iterate with rho = 0."""
+    g = load_golden("optima.npz")
+    p = oracle_params(20)
+    nb = 3
+    warm = np.zeros((nb, E.warm_size(20)))
+    for adaptive in (1, 0):
+        warm[:] = 0.0
+        hot = E.solve(p, g["n20_x0"][:nb], g["n20_ref"][:nb], g["n20_up"][:nb], warm=warm, warm_start=1, polish_passes=3, adaptive_rho=adaptive, **TIGHT)
+        cold = E.solve(p, g["n20_x0"][:nb], g["n20_ref"][:nb], g["n20_up"][:nb], polish_passes=3, adaptive_rho=adaptive, **TIGHT)
+        assert np.array_equal(hot["iters"], cold["iters"]) and np.array_equal(hot["status"], cold["status"])
+        assert np.array_equal(hot["u0"], cold["u0"])
+    warm[:, -1] = np.nan                                     # a poisoned slot is ignored as well
+    hot = E.solve(p, g["n20_x0"][:nb], g["n20_ref"][:nb], g["n20_up"][:nb], warm=warm, warm_start=1, polish_passes=3, **TIGHT)
+    cold = E.solve(p, g["n20_x0"][:nb], g["n20_ref"][:nb], g["n20_up"][:nb], polish_passes=3, **TIGHT)
+    assert np.array_equal(hot["iters"], cold["iters"])

@@ -181,8 +181,8 @@ def test_invalid_arguments_fail_loudly():
     with pytest.raises(ValueError):
         ctl.solve_batch(np.zeros((2, 4)), np.zeros((2, 21, 4)), u_prev=np.zeros((3, 2)))
     from rrt_mpc_b200 import MPCController
-    q = np.diag([4.0, 4.0, 0.6, 0.1]); q[0, 1] = q[1, 0] = 0.1
-    with pytest.raises(RuntimeError, match="non-diagonal"):
+    q = np.diag([4.0, 4.0, 0.6, 0.1]); q[0, 1] = q[1, 0] = 5.0            # indefinite
+    with pytest.raises(RuntimeError, match="positive semidefinite"):
         MPCController(dataclasses.replace(product_params(20), q=q)).solve(np.zeros(4), np.zeros((21, 4)))
 
 
@@ -210,3 +210,60 @@ def test_build_reference_batch_matches_reference_producer():
     ref, ref_len = ctl.build_reference_batch([d["path"]] * 3, 15.0)
     assert int(ref_len[0]) == 45
     assert np.abs(ref[1, :45].cpu().numpy() - d["ref_global"]).max() <= 1e-12 * 100
+
+
+def test_f_discrete_hook_within_1e12_of_reference():
+    """K_f (the closed loop's integrator) against outputs of the REAL vehicle_model.f_discrete (vehicle_model.py:11-21)."""
+    g = load_golden("vehicle_model.npz")
+    ctl = controller(20)
+    out = ctl.f_discrete_batch(g["x"], g["u"], g["dt_L"])
+    scale = np.maximum(1.0, np.abs(g["f"]))
+    assert (np.abs(out - g["f"]) <= 1e-12 * scale).all()
+    # default (dt, L) of the handle: config.py:79-81 wheelbase 2.8 m / 0.8 m per px, dt 0.1
+    from rrt_mpc_b200.vehicle_model import f_discrete
+    out = ctl.f_discrete_batch(g["x"][:16], g["u"][:16])
+    want = np.stack([f_discrete(g["x"][i], g["u"][i], 0.1, 2.8 / 0.8) for i in range(16)])
+    assert (np.abs(out - want) <= 1e-12 * np.maximum(1.0, np.abs(want))).all()
+
+
+@pytest.mark.parametrize("name,N,du,res", [("unit", 5, 0.15, 0.2), ("roll", 15, 0.15, 0.8), ("n20", 20, 0.15, 0.8), ("n50", 50, 0.02, 0.8)])
+def test_matches_what_the_reference_itself_returned(name, N, du, res):
+    """tests/golden/ref_qp.npz: return values of the UNMODIFIED reference MPCController.solve (executed through a recording
+    cvxpy stand-in and an exact QP solver, tests/golden/make_ref_qp.py).  Bar: u0 within 1e-5 at eps 1e-6."""
+    from rrt_mpc_b200 import MPCController, SolverSettings
+    g = load_golden("ref_qp.npz")
+    ctl = MPCController(product_params(N, du, res), SolverSettings(polish_passes=3, polish_retry=2, **TIGHT), max_batch=128)
+    for early in (False, True):
+        r = ctl.solve_batch(g[f"{name}_x0"], g[f"{name}_ref"], u_prev=g[f"{name}_up"],
+                            settings=SolverSettings(polish_passes=5 if early else 3, polish_retry=2, early_polish=early, **TIGHT))
+        assert (r.status == 1).all()
+        assert np.abs(r.u0 - g[f"{name}_u0"]).max() < 1e-5
+        assert np.abs(r.u0 - g[f"{name}_u0"]).max() < 1e-8
+        assert np.abs(r.Xp - g[f"{name}_X"]).max() < 1e-6 and np.abs(r.Up - g[f"{name}_U"]).max() < 1e-6
+
+
+def test_non_diagonal_weights_match_the_reference():
+    """Any PSD q / r / q_terminal (cp.quad_form, mpc_controller.py:74-75,112): the nd20 set of ref_qp.npz."""
+    from rrt_mpc_b200 import MPCController, SolverSettings
+    g = load_golden("ref_qp.npz")
+    p = dataclasses.replace(product_params(20), q=g["nd20_q"], r=g["nd20_r"], q_terminal=g["nd20_qn"])
+    ctl = MPCController(p, SolverSettings(polish_passes=3, polish_retry=2, **TIGHT), max_batch=64)
+    r = ctl.solve_batch(g["nd20_x0"], g["nd20_ref"], u_prev=g["nd20_up"])
+    assert (r.status == 1).all()
+    assert np.abs(r.u0 - g["nd20_u0"]).max() < 1e-8
+    assert np.abs(r.Xp - g["nd20_X"]).max() < 1e-6 and np.abs(r.Up - g["nd20_U"]).max() < 1e-6
+    u0, Xp, Up = ctl.solve(g["nd20_x0"][0], g["nd20_ref"][0], u_prev=g["nd20_up"][0])       # reference signature
+    assert np.abs(u0 - g["nd20_u0"][0]).max() < 1e-8
+
+
+def test_default_settings_regression_bound():
+    """MPCController(params).solve() at the reference's hard-coded settings (eps 1e-3, one polish): same loose contract as
+    the restated CPU path (tests/test_reference_pinned.py::test_reference_default_settings_regression_bound)."""
+    from rrt_mpc_b200 import MPCController, MPCConfig
+    g = load_golden("ref_qp.npz")
+    ctl = MPCController(MPCConfig().to_parameters(0.8), max_batch=128)                  # default SolverSettings
+    r = ctl.solve_batch(g["roll_x0"], g["roll_ref"], u_prev=g["roll_up"])
+    assert set(np.unique(r.status)) <= {1}
+    err = np.abs(r.u0 - g["roll_u0"])
+    assert np.median(err.max(axis=1)) <= 1e-6 and (err.max(axis=1) <= 1e-3).mean() >= 0.6
+    assert err[:, 0].max() <= 15.0 and err[:, 1].max() <= 0.1

@@ -81,3 +81,38 @@ def test_batch_tracking_result_roundtrip(tmp_path):
     assert np.array_equal(q.n_steps, r.n_steps) and np.array_equal(np.isnan(q.states), np.isnan(r.states))
     tr = q.result(0)                                       # what TrackingResult.states holds for vehicle 0 (artifacts.py:34-38)
     assert len(tr.states) == 3 and np.array_equal(tr.states[2], [8.0, 9.0, 10.0, 11.0])
+
+
+def test_solve_with_relaxation_retries_once_with_relaxed_problem():
+    """control_stage.py:33-56 on the host, with the controllers replaced by recorders (no GPU needed): a nominal failure
+    triggers exactly one retry with v_ref * 0.6 and du_bounds widened by (5.0, 0.05); the retry's triple is returned as is."""
+    from rrt_mpc_b200 import MPCConfig, TrajectoryTracker
+    calls = []
+
+    class Fake:
+        def __init__(self, params, outcome):
+            self.params, self.outcome = params, outcome
+
+        def solve(self, state, reference, *, u_prev=None):
+            calls.append((self.params, np.array(reference, copy=True), np.array(u_prev, copy=True)))
+            return self.outcome
+
+    tr = TrajectoryTracker(MPCConfig(), None)
+    base = MPCConfig().to_parameters(0.8)
+    ok = (np.array([1.0, 0.1]), np.zeros((4, 16)), np.zeros((2, 15)))
+    ref = np.tile(np.array([1.0, 2.0, 0.3, 10.0]), (16, 1))
+    # nominal success: one call, no retry
+    tr._controller = lambda params, key="base": Fake(params, ok)
+    out = tr._solve_with_relaxation(np.zeros(4), ref, np.array([0.5, 0.0]), base)
+    assert all(a is b for a, b in zip(out, ok)) and len(calls) == 1 and calls[0][0] is base
+    # nominal failure: retry with the relaxed problem, and its result (here again a failure) is returned unchanged
+    calls.clear()
+    outcomes = iter([(None, None, None), (None, None, None)])
+    tr._controller = lambda params, key="base": Fake(params, next(outcomes))
+    out = tr._solve_with_relaxation(np.zeros(4), ref, np.array([0.5, 0.0]), base)
+    assert out == (None, None, None) and len(calls) == 2
+    relaxed_params, relaxed_ref, up = calls[1]
+    assert relaxed_params.du_bounds == ((-17.0, 17.0), (-0.2, 0.2))                 # +-12 -> +-17, +-0.15 -> +-0.2
+    assert np.array_equal(relaxed_ref[:, 3], ref[:, 3] * 0.6) and np.array_equal(relaxed_ref[:, :3], ref[:, :3])
+    assert np.array_equal(ref[:, 3], np.full(16, 10.0))                             # the caller's window is not mutated
+    assert np.array_equal(up, [0.5, 0.0]) and relaxed_params.u_bounds == base.u_bounds

@@ -135,3 +135,24 @@ def test_oracle_track_default_scenario_reaches_goal():
     assert r["flags"] == 1 and 50 <= r["n_steps"] <= 80
     last = r["states"][r["n_steps"] - 1]
     assert np.hypot(last[0] - d["goal"][0], last[1] - d["goal"][1]) < 8.0
+
+
+def test_exact_optimum_certificate_recovers_the_reference_optima():
+    """tests/certificate.py (run on EVERY problem of the full-size GPU batches): from a perturbed candidate it must return
+    the optimum the reference itself returned (tests/golden/ref_qp.npz), for diagonal and non-diagonal weights."""
+    from certificate import exact_optimum, lin_from_hook
+    g = load_golden("ref_qp.npz")
+    import dataclasses
+    for name, N, du in (("n20", 20, 0.15), ("n50", 50, 0.02), ("roll", 15, 0.15), ("nd20", 20, 0.15)):
+        p = oracle_params(N, du)
+        if name == "nd20":
+            p = dataclasses.replace(p, q=g["nd20_q"], r=g["nd20_r"], q_terminal=g["nd20_qn"])
+        x0, ref, up, U = g[f"{name}_x0"], g[f"{name}_ref"], g[f"{name}_up"], g[f"{name}_U"]
+        lins = [O.linearize_window(ref[b], p) for b in range(len(ref))]
+        refu = np.stack([l[0] for l in lins]); A = np.stack([l[1] for l in lins]); Bm = np.stack([l[2] for l in lins])
+        rng = np.random.default_rng(0)
+        for scale in (0.0, 1e-6, 1e-2):
+            c = exact_optimum(p, x0, refu, up, U + rng.normal(size=U.shape) * scale, lin_from_hook(A, Bm))
+            assert c["settled"].all()
+            assert np.abs(c["U"] - U).max() < 1e-8 and np.abs(c["X"] - g[f"{name}_X"]).max() < 1e-7
+            assert c["newton_steps"].max() <= (1 if scale == 0.0 else 2 if scale == 1e-6 else 40)

@@ -1,3 +1,4 @@
+#include <string.h>
 // Per-phase cycle breakdown of one warp solving one real problem (dev tool): tags set by solve_problem.
 #include <cstdio>
 #include <cstdlib>
@@ -36,7 +37,8 @@ __global__ void k(Params p, Settings s, const double* x0, const double* ref, con
 int main(int argc, char** argv) {
   int N = argc > 1 ? atoi(argv[1]) : 50;
   Params p; p.L = 3.5; p.dt = 0.1; p.N = N; double q[4] = {4, 4, 0.6, 0.1}, qn[4] = {8, 8, 1, 0.2};
-  for (int i = 0; i < 4; ++i) { p.q[i] = q[i]; p.qn[i] = qn[i]; } p.r[0] = 0.03; p.r[1] = 0.25;
+  memset(p.pq, 0, sizeof p.pq); memset(p.pqn, 0, sizeof p.pqn); memset(p.pr, 0, sizeof p.pr);
+  for (int i = 0; i < 4; ++i) { p.pq[i][i] = 2.0 * q[i]; p.pqn[i][i] = 2.0 * qn[i]; } p.pr[0][0] = 0.06; p.pr[1][1] = 0.5;
   p.u_lo[0] = -35; p.u_hi[0] = 35; p.u_lo[1] = -0.6; p.u_hi[1] = 0.6; p.v_lo = 0; p.v_hi = 90;
   p.du_lo[0] = -12; p.du_hi[0] = 12; p.du_lo[1] = -0.02; p.du_hi[1] = 0.02; p.w_v = 1e3; p.w_u = 5e2; p.w_du = 5e2;
   Settings s; s.eps_abs = s.eps_rel = 1e-6; s.rho0 = 0.1; s.alpha = 1.6; s.sigma = 1e-6; s.adaptive_rho_tolerance = 5; s.rho_eq_factor = 1e3;
