@@ -97,14 +97,21 @@ __global__ void mpc_linearize_kernel(Params p, int batch, const double* ref, dou
 // K_f: batched f_discrete hook (parity at 1e-12 against vehicle_model.f_discrete, vehicle_model.py:11-21); the very
 // function the closed loop integrates with.  dt_L: optional per-sample (dt, wheelbase_px) pairs, else the handle's.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void f_discrete_dev(const Params& p, const double* x, const double* u, double* out);
-__global__ void mpc_f_discrete_kernel(Params p, int batch, const double* x, const double* u, const double* dt_L, double* out) {
+__device__ __forceinline__ void f_discrete_vals(double dt, double L, const double* x, const double* u, double* out) {
+  // vehicle_model.py:11-21 (beta = 0.0 is added to the yaw there)
+  const double yaw = x[2], v = x[3];
+  out[0] = x[0] + dt * v * cos(yaw + 0.0);
+  out[1] = x[1] + dt * v * sin(yaw + 0.0);
+  out[2] = yaw + dt * (v / L) * tan(u[1]);
+  out[3] = v + dt * u[0];
+}
+__global__ void mpc_f_discrete_kernel(double dt0, double L0, int batch, const double* x, const double* u, const double* dt_L, double* out) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
-  Params q = p;
-  if (dt_L) { q.dt = dt_L[2 * (size_t)b]; q.L = dt_L[2 * (size_t)b + 1]; }
+  const double dt = dt_L ? dt_L[2 * (size_t)b] : dt0;
+  const double L = dt_L ? dt_L[2 * (size_t)b + 1] : L0;
   double o[4];
-  f_discrete_dev(q, x + 4 * (size_t)b, u + 2 * (size_t)b, o);
+  f_discrete_vals(dt, L, x + 4 * (size_t)b, u + 2 * (size_t)b, o);
 #pragma unroll
   for (int i = 0; i < 4; ++i) out[4 * (size_t)b + i] = o[i];
 }
@@ -121,12 +128,7 @@ struct RolloutArgs {
 };
 
 __device__ __forceinline__ void f_discrete_dev(const Params& p, const double* x, const double* u, double* out) {
-  // vehicle_model.py:11-21
-  double yaw = x[2], v = x[3];
-  out[0] = x[0] + p.dt * v * cos(yaw + 0.0);
-  out[1] = x[1] + p.dt * v * sin(yaw + 0.0);
-  out[2] = yaw + p.dt * (v / p.L) * tan(u[1]);
-  out[3] = v + p.dt * u[0];
+  f_discrete_vals(p.dt, p.L, x, u, out);
 }
 
 // One vehicle, all steps (TrajectoryTracker.track loop body, control_stage.py:100-150), generic in the execution policy
@@ -586,7 +588,7 @@ int cudampc_f_discrete_batch(cudampc_handle* h, int batch, const double* x_dev, 
   if (batch < 0 || !x_dev || !u_dev || !out_dev) return fail(h, CUDAMPC_ERR_INVALID, "%s", "f_discrete_batch: NULL pointer or negative batch");
   if (batch == 0) return CUDAMPC_OK;
   ON_DEVICE(h);
-  mpc_f_discrete_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->p, batch, x_dev, u_dev, dt_L_dev, out_dev);
+  mpc_f_discrete_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->p.dt, h->p.L, batch, x_dev, u_dev, dt_L_dev, out_dev);
   h->launches++;
   CU(h, cudaGetLastError());
   return CUDAMPC_OK;

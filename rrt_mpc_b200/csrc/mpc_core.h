@@ -136,7 +136,13 @@ struct View {
   int fpad, xpad;    // bank-conflict pads of the bottom half (layout_pads)
   MPC_HD double* hdr() const { return base; }
   MPC_HD int* act() const { return reinterpret_cast<int*>(base + H_ACT); }  // [N+1] stage masks + [N+1]=init rows
-  MPC_HD double* rec(int k) const { return base + hdr_size(N) + k * SR; }
+  // records are stored even stages first, then the odd ones: the ADMM phases run one parity at a time, and lanes striding
+  // over the stages of one parity then stay SR (odd) doubles apart - conflict-free
+  MPC_HD double* rec(int k) const { return base + hdr_size(N) + ((k & 1) ? (N / 2 + 1) + (k >> 1) : (k >> 1)) * SR; }
+  // natural (untwisted) rhs / solution rows of the odd-even block solve: row k of the 6(N+1)-vector, same parity split;
+  // row N+1 is a row of zeros
+  MPC_HD double* nx(int k) const { return bx_base() + BXS * ((k & 1) ? (N / 2 + 1) + (k >> 1) : (k >> 1)); }
+  MPC_HD double* nx_zero() const { return bx_base() + BXS * (N + 1); }
   MPC_HD double* bx_base() const { return base + bx_offset(N); }
   MPC_HD double* scratch() const { return bx_base(); }                       // >= N+1 doubles, free before the first solve
   MPC_HD HalfView top() const { return HalfView{bx_base() + BXS, base + band_offset(N), half_top(N)}; }
@@ -909,15 +915,21 @@ MPC_HD void admm_rhs_stage(const View& w, const Params& p, const Settings& s, do
 // loops over groups and rows unrolled at compile time, bounds hoisted, one-sided clips instead of two-sided,
 // and v + alpha (z~ - z) in place of alpha z~ + (1-alpha) z + (v - z).
 // ----------------------------------------------------------------------------------------------
+}  // namespace mpc
+#include "mpc_oe.h"
+namespace mpc {
+
 struct IterConst {
   double rho, rho_eq, alpha, sigma, ra;     // ra = rho_eq * alpha
   double lo[5], hi[5], mssinv[5];           // soft-group bounds (stage k > 0) and 1 / (2w + sigma + 3 rho)
   double ps_[5];                            // P entries of the slacks (2w)
   double up0, up1;                          // u_prev: shifts the rate bounds of stage 0
+  double kap;                               // 2 rho: coupling of consecutive inputs through the rate groups
 };
 MPC_HD IterConst iter_const(const View& w, const Params& p, const Settings& s, double rho) {
   IterConst c;
   c.rho = rho; c.rho_eq = s.rho_eq_factor * rho; c.alpha = s.alpha; c.sigma = s.sigma; c.ra = c.rho_eq * s.alpha;
+  c.kap = 2.0 * rho;
   c.lo[0] = p.v_lo; c.hi[0] = p.v_hi;
   c.lo[1] = p.u_lo[0]; c.hi[1] = p.u_hi[0]; c.lo[2] = p.u_lo[1]; c.hi[2] = p.u_hi[1];
   c.lo[3] = p.du_lo[0]; c.hi[3] = p.du_hi[0]; c.lo[4] = p.du_lo[1]; c.hi[4] = p.du_hi[1];
@@ -949,16 +961,12 @@ MPC_HD void bx_load6(const View& w, int k, double* x) {
   for (int j = 0; j < 6; ++j) x[j] = p[j * st];
 }
 
-// A1: consume x-tilde / s-tilde, relax x and s, update the row states
-MPC_HD void admm_update_fast(const View& w, const Params& p, const IterConst& c, int k) {
+// A1: consume x-tilde / s-tilde, relax x and s, update the row states.  xt = x-tilde of stage k, xn = of stage k+1 (read
+// when k < N), (ua, ud) = the inputs of stage k-1 (0 for k = 0).
+MPC_HD void admm_update_vals(const View& w, const Params& p, const IterConst& c, int k, const double* xt, const double* xn, double ua, double ud) {
   const int N = w.N;
   double* rc = w.rec(k);
-  double xt[6], xn[6], xp[6];
-  bx_load6(w, k, xt);
   const bool reg = k < N;
-  if (reg) bx_load6(w, k + 1, xn);
-  double ua = 0.0, ud = 0.0;
-  if (k > 0 && reg) { bx_load6(w, k - 1, xp); ua = xp[4]; ud = xp[5]; }
   const double off0 = k == 0 ? c.up0 : 0.0, off1 = k == 0 ? c.up1 : 0.0;
   const double gt[5] = {xt[3], xt[4], xt[5], xt[4] - ua, xt[5] - ud};
   const double offs[5] = {0.0, 0.0, 0.0, off0, off1};
@@ -995,8 +1003,8 @@ MPC_HD void admm_update_fast(const View& w, const Params& p, const IterConst& c,
     if (j < 4 || reg) { const double xo = rc[R_XU + j]; rc[R_XU + j] = fma(c.alpha, xt[j] - xo, xo); }
 }
 
-// A2: t = rho z - y of every row from the new state, s-tilde, banded right-hand side
-MPC_HD void admm_rhs_fast(const View& w, const Params& p, const IterConst& c, int k) {
+// A2: t = rho z - y of every row from the new state, s-tilde, right-hand side of stage k -> val[6]
+MPC_HD void admm_rhs_vals(const View& w, const Params& p, const IterConst& c, int k, double* val) {
   const int N = w.N;
   double* rc = w.rec(k);
   const bool reg = k < N;
@@ -1046,18 +1054,66 @@ MPC_HD void admm_rhs_fast(const View& w, const Params& p, const IterConst& c, in
       }
     }
   }
-  int rev; double* b = bx_ptr(w, k, rev);
 #pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    double val = 0.0;
-    if (j < 4 || reg) val = c.sigma * rc[R_XU + j] - (j < 4 ? rc[R_Q + j] : 0.0) + out[j];
-    b[rev ? 5 - j : j] = val;
-  }
-  if (k == mid_stage(N)) {
-    double* bb = w.bottom().bx(N - k);
+  for (int j = 0; j < 6; ++j) val[j] = (j < 4 || reg) ? c.sigma * rc[R_XU + j] - (j < 4 ? rc[R_Q + j] : 0.0) + out[j] : 0.0;
+}
+
+// The two phases as the iteration loop runs them, ONE PARITY OF STAGES AT A TIME, with the stage-parallel parts of the
+// odd-even block solve (mpc_oe.h) fused in:
+//   rhs,    odd  k: b_k -> t_k = D_k^-1 b_k                                   (rows of the even neighbours are not touched)
+//   rhs,    even k: b_k -> b'_k = b_k - E_k t_{k-1} - E_{k+1}' t_{k+1}        (after the odd pass)
+//   update, odd  k: x~_k = t_k - D_k^-1 (E_k x~_{k-1} + E_{k+1}' x~_{k+1}), then A1(k)   (after the sweeps over the even stages)
+//   update, even k: A1(k)                                                     (after the odd pass: it reads x~_{k-1}, x~_{k+1})
+MPC_HD void admm_rhs_stage_oe(const View& w, const Params& p, const IterConst& c, const OEView& oe, int k) {
+  const int N = w.N;
+  double val[6];
+  admm_rhs_vals(w, p, c, k, val);
+  if (k & 1) {
+    double di[OE_SYM], t[6];
+    sym_load(oe.dinv + OE_SYM * (k >> 1), di);
+    symv6(di, val, t);
+    row_store(w.nx(k), t);
+  } else {
+    double t[6], y[6];
+    if (k >= 1) {
+      row_load(w.nx(k - 1), t);
+      cross_mul(w.rec(k - 1) + R_LIN, p.dt, c.rho_eq, c.kap, k < N, t, y);
 #pragma unroll
-    for (int j = 0; j < 6; ++j) bb[j] = 0.0;
+      for (int j = 0; j < 6; ++j) val[j] -= y[j];
+    }
+    if (k + 1 <= N) {
+      row_load(w.nx(k + 1), t);
+      cross_mul_t(w.rec(k) + R_LIN, p.dt, c.rho_eq, c.kap, k + 1 < N, t, y);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) val[j] -= y[j];
+    }
+    row_store(w.nx(k), val);
   }
+}
+MPC_HD void admm_update_stage_oe(const View& w, const Params& p, const IterConst& c, const OEView& oe, int k) {
+  const int N = w.N;
+  double xt[6], xn[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, xp[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (k >= 1) row_load(w.nx(k - 1), xp);
+  if (k + 1 <= N) row_load(w.nx(k + 1), xn);
+  if (k & 1) {
+    double di[OE_SYM], t[6], v[6], y[6], u[6];
+    row_load(w.nx(k), t);
+    cross_mul(w.rec(k - 1) + R_LIN, p.dt, c.rho_eq, c.kap, k < N, xp, v);
+    if (k + 1 <= N) {
+      cross_mul_t(w.rec(k) + R_LIN, p.dt, c.rho_eq, c.kap, k + 1 < N, xn, y);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) v[j] += y[j];
+    }
+    sym_load(oe.dinv + OE_SYM * (k >> 1), di);
+    symv6(di, v, u);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) xt[j] = t[j] - u[j];
+    row_store(w.nx(k), xt);
+  } else {
+    row_load(w.nx(k), xt);
+  }
+  const bool inputs_before = k > 0 && k < N;
+  admm_update_vals(w, p, c, k, xt, xn, inputs_before ? xp[4] : 0.0, inputs_before ? xp[5] : 0.0);
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -76,6 +76,7 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
   // code instead of four keeps the kernel's hot instruction footprint small.
   Mode mode = admm_mode(rho, s);
   IterConst ic = iter_const(w, p, s, rho);
+  const OEView oe = oe_view(w);            // odd-even block solve of the ADMM iterations (mpc_oe.h)
   bool need_factor = true;
 
   // ---- ADMM + polish --------------------------------------------------------------------------
@@ -164,15 +165,24 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
   while (!finished) {
     if (need_factor) {
       mode = admm_mode(rho, s);
-      ex.tag(4); ex.stages(NS, [&](int k) { assemble_stage(w, p, mode, k); });
-      ex.tag(5); ex.factor(w); ++n_fac;
+      ex.tag(5); ex.oe_factor(w, p, mode, oe); ++n_fac;
       ic = iter_const(w, p, s, rho);
       need_factor = false;
     }
-    ex.tag(6); ex.stages(NS, [&](int k) { admm_rhs_fast(w, p, ic, k); });
+    // one ADMM iteration: right-hand side (odd stages, then even), sweeps over the even stages, update (odd, then even)
+    // (the two parities of a phase share ONE copy of the phase's code: the iteration loop has to stay inside the
+    // instruction cache - 32 KB of L1.5 per SM - also when the resident problems are at different places of the solve)
+    ex.tag(6);
+#pragma unroll 1
+    for (int par = 1; par >= 0; --par) ex.stages_par(NS, par, [&](int k) { admm_rhs_stage_oe(w, p, ic, oe, k); });
     ++it;
-    ex.tag(1); ex.solve_iter(w); ++n_solve;
-    ex.tag(2); ex.stages(NS, [&](int k) { admm_update_fast(w, p, ic, k); });
+    ex.tag(1);
+    ex.oe_forward(w, oe);
+    ex.stages_par(NS, 0, [&](int k) { oe_diag_stage(w, oe, k); });
+    ex.oe_backward(w, oe); ++n_solve;
+    ex.tag(2);
+#pragma unroll 1
+    for (int par = 1; par >= 0; --par) ex.stages_par(NS, par, [&](int k) { admm_update_stage_oe(w, p, ic, oe, k); });
     const bool last = it >= s.max_iter;
     const bool check = last || ((s.check_termination > 0) && (it % s.check_termination == 0));
     const bool adapt = !last && s.adaptive_rho && (s.adaptive_rho_interval > 0) && (it % s.adaptive_rho_interval == 0);

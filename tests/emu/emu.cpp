@@ -26,9 +26,23 @@ struct EmuExec {
     stages(n, [&](int k) { a |= f(k); });
     return a;
   }
+  template <class F> void stages_par(int n, int par, F f) {
+    if (!reverse) for (int k = par; k < n; k += 2) f(k);
+    else for (int k = ((n - 1 - par) / 2) * 2 + par; k >= 0; k -= 2) f(k);
+  }
   void factor(const View& w) { factor_band(w); }
   void solve(const View& w) { chain_solve(w); }
-  void solve_iter(const View& w) { chain_solve_rolling(w); }   // same arithmetic, the kernel's prefetch order
+  // odd-even block solve of the ADMM iterations: the same pieces the CUDA policy runs with lanes over stages / two chain lanes
+  void oe_factor(const View& w, const Params& p, const Mode& m, const OEView& oe) {
+    stages_par(w.N + 1, 1, [&](int k) { oe_factor_odd(w, p, m, oe, k); });
+    stages_par(w.N + 1, 0, [&](int k) { oe_factor_even(w, p, m, oe, k); });
+    double Ut[21], Ub[21];
+    if (!reverse) { oe_factor_half(oe_half(w, oe, false), Ut); oe_factor_half(oe_half(w, oe, true), Ub); }
+    else { oe_factor_half(oe_half(w, oe, true), Ub); oe_factor_half(oe_half(w, oe, false), Ut); }
+    oe_factor_middle(oe, Ut, Ub);
+  }
+  void oe_forward(const View& w, const OEView&) { oe_forward_seq(w); }
+  void oe_backward(const View& w, const OEView&) { oe_backward_seq(w); }
 };
 
 extern "C" {
