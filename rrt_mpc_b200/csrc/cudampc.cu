@@ -16,49 +16,9 @@
 #include <new>
 
 #include "../../include/cudampc.h"
-#include "mpc_exec.cuh"
+#include "mpc_kernels.cuh"
 
 using namespace mpc;
-
-struct BatchArgs {
-  const double* x0; const double* ref; const double* u_prev;
-  double* warm; double* scratch;
-  double* u0; double* Xp; double* Up; int* status; int* iters; double* pri; double* dua; int* info;
-  int* counter;
-  int batch;
-};
-
-// ------------------------------------------------------------------------------------------------
-// K_solve: batched MPCController.solve.  The CTA holds P problems, each owned by a group of WPP warps (GroupExec).
-// <256,1>: P <= 8 one-warp groups, 255 registers; <128,2>: P <= 2 two-warp groups for long horizons.
-// ------------------------------------------------------------------------------------------------
-template <int MAXT, int WPP>
-__global__ void __launch_bounds__(MAXT) mpc_solve_kernel(Params p, Settings s, BatchArgs a, int P, int F) {
-  extern __shared__ double smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int N = p.N;
-  GroupShared* sh = reinterpret_cast<GroupShared*>(smem + (size_t)P * F) + warp / WPP;
-  int fpad, xpad; layout_pads(N, fpad, xpad);
-  View w{smem + (size_t)(warp / WPP) * F, N, fpad, xpad};
-  GroupExec<WPP> ex{lane, warp, sh};
-  const int ws = warm_size(N);
-  for (int b = ex.fetch(a.counter); b < a.batch; b = ex.fetch(a.counter)) {
-    ProblemIO io;
-    io.x0 = a.x0 + 4 * (size_t)b;
-    io.ref = RefWin{a.ref + (size_t)4 * (N + 1) * b, 0, N + 1, 1.0};
-    io.u_prev = a.u_prev ? a.u_prev + 2 * (size_t)b : nullptr;
-    io.warm = a.warm + (size_t)ws * b;
-    io.scratch = a.scratch + (size_t)ws * b;
-    io.u0 = a.u0 + 2 * (size_t)b;
-    io.Xp = a.Xp + (size_t)4 * (N + 1) * b;
-    io.Up = a.Up + (size_t)2 * N * b;
-    io.status = a.status + b; io.iters = a.iters + b;
-    io.pri_res = a.pri ? a.pri + b : nullptr; io.dua_res = a.dua ? a.dua + b : nullptr;
-    io.info = a.info ? a.info + 4 * (size_t)b : nullptr;
-    solve_problem(ex, w, p, s, io);
-    ex.group_sync();
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // K_lin: batched linearisation hook (parity at 1e-12 against vehicle_model.linearize)
@@ -97,14 +57,6 @@ __global__ void mpc_linearize_kernel(Params p, int batch, const double* ref, dou
 // K_f: batched f_discrete hook (parity at 1e-12 against vehicle_model.f_discrete, vehicle_model.py:11-21); the very
 // function the closed loop integrates with.  dt_L: optional per-sample (dt, wheelbase_px) pairs, else the handle's.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void f_discrete_vals(double dt, double L, const double* x, const double* u, double* out) {
-  // vehicle_model.py:11-21 (beta = 0.0 is added to the yaw there)
-  const double yaw = x[2], v = x[3];
-  out[0] = x[0] + dt * v * cos(yaw + 0.0);
-  out[1] = x[1] + dt * v * sin(yaw + 0.0);
-  out[2] = yaw + dt * (v / L) * tan(u[1]);
-  out[3] = v + dt * u[0];
-}
 __global__ void mpc_f_discrete_kernel(double dt0, double L0, int batch, const double* x, const double* u, const double* dt_L, double* out) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
@@ -114,108 +66,6 @@ __global__ void mpc_f_discrete_kernel(double dt0, double L0, int batch, const do
   f_discrete_vals(dt, L, x + 4 * (size_t)b, u + 2 * (size_t)b, o);
 #pragma unroll
   for (int i = 0; i < 4; ++i) out[4 * (size_t)b + i] = o[i];
-}
-
-// ------------------------------------------------------------------------------------------------
-// K_rollout: TrajectoryTracker.track for a batch of vehicles, all steps on the device
-// ------------------------------------------------------------------------------------------------
-struct RolloutArgs {
-  const double* ref_global; const int* ref_len; int ref_stride;
-  const double* state0; const double* goal;
-  double* warm; double* scratch; double* work;   // work: per vehicle 16 doubles (state, u_prev, u0 out) + Xp/Up scratch
-  double* states; double* controls; int* n_steps; int* flags; int* step_status; int* step_iters;
-  int* counter; int batch;
-};
-
-__device__ __forceinline__ void f_discrete_dev(const Params& p, const double* x, const double* u, double* out) {
-  f_discrete_vals(p.dt, p.L, x, u, out);
-}
-
-// One vehicle, all steps (TrajectoryTracker.track loop body, control_stage.py:100-150), generic in the execution policy
-template <class Exec>
-__device__ __forceinline__ void rollout_vehicle(Exec& ex, const View& w, const Params& p, const Settings& s,
-                                                const cudampc_rollout_cfg& cfg, const RolloutArgs& a, int b) {
-  const int N = p.N;
-  const int ws = warm_size(N);
-  const int wk = 16 + 4 * (N + 1) + 2 * N;   // per-vehicle global scratch
-  const double nan_ = __longlong_as_double(0x7ff8000000000000LL);
-  double* wkb = a.work + (size_t)wk * b;     // [0..3] state, [4..5] u_prev, [6..7] u0, [10..11] status/iters (int), 16.. Xp, Up
-  const double* refg = a.ref_global + (size_t)4 * a.ref_stride * b;
-  const int len = a.ref_len[b];
-  if (len < 1) {                                           // control_stage.py:71-72 raises for an empty path; per vehicle: aborted, no steps
-    const int T0 = cfg.sim_steps;
-    ex.stages(T0 * 4, [&](int i) { a.states[(size_t)T0 * b * 4 + i] = nan_; });
-    if (a.controls) ex.stages(T0 * 2, [&](int i) { a.controls[(size_t)T0 * b * 2 + i] = nan_; });
-    if (a.step_status) ex.stages(T0, [&](int i) { a.step_status[(size_t)T0 * b + i] = 0; });
-    if (a.step_iters) ex.stages(T0, [&](int i) { a.step_iters[(size_t)T0 * b + i] = 0; });
-    ex.single([&]() { a.n_steps[b] = 0; a.flags[b] = 2; });
-    return;
-  }
-  ex.single([&]() {
-    for (int i = 0; i < 4; ++i) wkb[i] = a.state0[4 * (size_t)b + i];
-    wkb[4] = 0.0; wkb[5] = 0.0;
-  });
-  int path_idx = 0, flags = 0, nst = 0;
-  for (int step = 0; step < cfg.sim_steps; ++step) {
-    int* st_out = a.step_status ? a.step_status + (size_t)cfg.sim_steps * b + step : reinterpret_cast<int*>(wkb + 10);
-    int* it_out = a.step_iters ? a.step_iters + (size_t)cfg.sim_steps * b + step : reinterpret_cast<int*>(wkb + 10) + 1;
-    ProblemIO io;
-    io.x0 = wkb; io.u_prev = wkb + 4;
-    io.ref = RefWin{refg, path_idx, len, 1.0};
-    io.warm = a.warm + (size_t)ws * b; io.scratch = a.scratch + (size_t)ws * b;
-    io.u0 = wkb + 6; io.Xp = wkb + 16; io.Up = wkb + 16 + 4 * (N + 1);
-    io.status = st_out; io.iters = it_out; io.pri_res = nullptr; io.dua_res = nullptr; io.info = nullptr;
-    Settings ss = s;
-    ss.warm_start = (s.warm_start && step > 0) ? 1 : 0;
-    solve_problem(ex, w, p, ss, io);
-    ex.group_sync();
-    int status = *st_out;
-    if (status != STATUS_SOLVED && status != STATUS_SOLVED_INACCURATE && cfg.relax_on_failure) {
-      // control_stage.py:45-56: v_ref *= 0.6, du_bounds widened, one cold retry
-      Params pr = p;
-      pr.du_lo[0] -= cfg.relax_da; pr.du_hi[0] += cfg.relax_da;
-      pr.du_lo[1] -= cfg.relax_ddelta; pr.du_hi[1] += cfg.relax_ddelta;
-      io.ref.vscale = cfg.relax_v_scale;
-      ss.warm_start = 0;
-      solve_problem(ex, w, pr, ss, io);
-      ex.group_sync();
-      status = *st_out;
-      flags |= 4;
-    }
-    if (status != STATUS_SOLVED && status != STATUS_SOLVED_INACCURATE) { flags |= 2; break; }
-    // integrate, carry u_prev, path index rule, goal test (control_stage.py:127-150)
-    double xn[4];
-    f_discrete_dev(p, wkb, wkb + 6, xn);
-    const double u0a = wkb[6], u0d = wkb[7];
-    ex.group_sync();
-    ex.single([&]() {
-      for (int i = 0; i < 4; ++i) { wkb[i] = xn[i]; a.states[((size_t)cfg.sim_steps * b + step) * 4 + i] = xn[i]; }
-      wkb[4] = u0a; wkb[5] = u0d;
-      if (a.controls) { a.controls[((size_t)cfg.sim_steps * b + step) * 2] = u0a; a.controls[((size_t)cfg.sim_steps * b + step) * 2 + 1] = u0d; }
-    });
-    nst = step + 1;
-    if (path_idx < len - 2) {
-      double dx = xn[0] - refg[4 * (size_t)path_idx], dy = xn[1] - refg[4 * (size_t)path_idx + 1];
-      if (dx * dx + dy * dy > cfg.advance_dist2) path_idx += 1;
-    }
-    if (hypot(xn[0] - a.goal[2 * (size_t)b], xn[1] - a.goal[2 * (size_t)b + 1]) < cfg.goal_radius) { flags |= 1; break; }
-  }
-  // rows after the vehicle stopped
-  const int T = cfg.sim_steps, skip = nst + ((flags & 2) ? 1 : 0);
-  ex.stages(T * 4, [&](int i) { if (i >= nst * 4) a.states[(size_t)T * b * 4 + i] = nan_; });
-  if (a.controls) ex.stages(T * 2, [&](int i) { if (i >= nst * 2) a.controls[(size_t)T * b * 2 + i] = nan_; });
-  if (a.step_status) ex.stages(T, [&](int i) { if (i >= skip) a.step_status[(size_t)T * b + i] = 0; });
-  if (a.step_iters) ex.stages(T, [&](int i) { if (i >= skip) a.step_iters[(size_t)T * b + i] = 0; });
-  ex.single([&]() { a.n_steps[b] = nst; a.flags[b] = flags; });
-}
-
-__global__ void __launch_bounds__(32) mpc_rollout_kernel(Params p, Settings s, cudampc_rollout_cfg cfg, RolloutArgs a) {
-  extern __shared__ double smem[];
-  const int lane = threadIdx.x & 31;
-  int fpad, xpad; layout_pads(p.N, fpad, xpad);
-  View w{smem, p.N, fpad, xpad};
-  GroupExec<1> ex{lane, 0, nullptr};
-  for (int b = ex.fetch(a.counter); b < a.batch; b = ex.fetch(a.counter)) rollout_vehicle(ex, w, p, s, cfg, a, b);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -321,11 +171,22 @@ struct cudampc_handle {
   size_t in_doubles, out_doubles;
   int sms, smem_bytes, roll_per_sm;   // K_rollout: one-warp CTAs of smem_bytes each, roll_per_sm resident per SM
   int grp_P, grp_wpp, grp_smem;        // K_solve: one CTA per SM with grp_P groups of grp_wpp warps
+  int variant;                         // SolveVariant
+  unsigned long long* tags;            // dev builds (MPC_TIMING): per-tag cycle counters
   long long launches;
   char err[512];
 };
 
 static char g_create_err[512] = "";
+
+// launchers of the kernel instantiations (mpc_kernels_tu.cu, one translation unit each)
+cudaError_t solve_set_smem_0(int), solve_set_smem_1(int);
+void solve_launch_0(int, int, int, cudaStream_t, const Params&, const Settings&, const BatchArgs&, int, int);
+void solve_launch_1(int, int, int, cudaStream_t, const Params&, const Settings&, const BatchArgs&, int, int);
+cudaError_t solve_set_smem(int v, int bytes) { return v == SOLVE_W1 ? solve_set_smem_0(bytes) : solve_set_smem_1(bytes); }
+void solve_launch(int v, int grid, int threads, int smem, cudaStream_t st, const Params& p, const Settings& s, const BatchArgs& a, int P, int F) {
+  if (v == SOLVE_W1) solve_launch_0(grid, threads, smem, st, p, s, a, P, F); else solve_launch_1(grid, threads, smem, st, p, s, a, P, F);
+}
 
 // Every entry point runs on the handle's device and leaves the caller's current device as it found it.
 struct DeviceGuard {
@@ -476,24 +337,25 @@ int cudampc_create(const cudampc_params* params, int max_batch, int device, cuda
   const int optin = (int)prop.sharedMemPerBlockOptin;
   if (h->smem_bytes + (int)sizeof(GroupShared) > optin) { delete h; return fail(nullptr, CUDAMPC_ERR_UNSUPPORTED, "%s", "horizon too long for one problem per 227 KB of shared memory"); }
   // K_rollout: one-warp CTAs
-  e = cudaFuncSetAttribute(mpc_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes);
+  e = rollout_set_smem(h->smem_bytes);
   int occ = 0;
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mpc_rollout_kernel, 32, h->smem_bytes);
+  if (e == cudaSuccess) e = rollout_occupancy(h->smem_bytes, &occ);
   if (e != cudaSuccess || occ < 1) { delete h; return fail(nullptr, CUDAMPC_ERR_CUDA, "CUDA failure: %s", cudaGetErrorString(e)); }
   h->roll_per_sm = occ;
   // K_solve: one CTA per SM with P independent groups.  P <= 8: with more resident warps the 255-register budget of the
   // driver would have to shrink.  Two warps per group pay off only when few problems fit (long horizons: the SM is
-  // latency-bound there); at P >= 3 the sub-partitions are issue-bound and the extra barriers cost more than they save.
+  // latency-bound there); at P >= 3 the extra barriers cost more than the second warp saves (measured again in round 2:
+  // branch item-form-experiment).
   {
     int P = (optin - 64) / (F * (int)sizeof(double) + (int)sizeof(GroupShared));
-    if (P > 8) P = 8;            // measured at N=20: 12 groups under a 168-register cap gain 5 % without early polish, lose 15 % with it
+    if (P > 8) P = 8;
     if (const char* pe = getenv("CUDAMPC_P")) { int v = atoi(pe); if (v >= 1 && v < P) P = v; }   // tuning knobs
     h->grp_P = P;
     h->grp_wpp = (P <= 2 && p.N + 1 > 32) ? 2 : 1;
     if (const char* we = getenv("CUDAMPC_WPP")) { int v = atoi(we); if (v == 1 || (v == 2 && P <= 2)) h->grp_wpp = v; }
+    h->variant = h->grp_wpp == 2 ? SOLVE_W2 : SOLVE_W1;
     h->grp_smem = P * (F * (int)sizeof(double) + (int)sizeof(GroupShared)) + 16;
-    e = h->grp_wpp == 2 ? cudaFuncSetAttribute(mpc_solve_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->grp_smem)
-                        : cudaFuncSetAttribute(mpc_solve_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->grp_smem);
+    e = solve_set_smem(h->variant, h->grp_smem);
     if (e != cudaSuccess) { delete h; return fail(nullptr, CUDAMPC_ERR_CUDA, "CUDA failure: %s", cudaGetErrorString(e)); }
   }
   const size_t ws = (size_t)warm_size(p.N) * max_batch * sizeof(double);
@@ -504,6 +366,10 @@ int cudampc_create(const cudampc_params* params, int max_batch, int device, cuda
   if (e == cudaSuccess) e = cudaMalloc(&h->scratch, ws);
   if (e == cudaSuccess) e = cudaMalloc(&h->work, wk);
   if (e == cudaSuccess) e = cudaMalloc(&h->counter, sizeof(int));
+#ifdef MPC_TIMING
+  if (e == cudaSuccess) e = cudaMalloc(&h->tags, sizeof(unsigned long long) * 32);
+  if (e == cudaSuccess) e = cudaMemset(h->tags, 0, sizeof(unsigned long long) * 32);
+#endif
   if (e == cudaSuccess) e = cudaMalloc(&h->d_in, h->in_doubles * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&h->d_out, h->out_doubles * sizeof(double));
   if (e == cudaSuccess) e = cudaMallocHost(&h->h_in, h->in_doubles * sizeof(double));
@@ -521,7 +387,7 @@ int cudampc_create(const cudampc_params* params, int max_batch, int device, cuda
 int cudampc_destroy(cudampc_handle* h) {
   if (!h) return CUDAMPC_OK;
   DeviceGuard guard_(h->device);
-  cudaFree(h->warm); cudaFree(h->scratch); cudaFree(h->work); cudaFree(h->counter);
+  cudaFree(h->warm); cudaFree(h->scratch); cudaFree(h->work); cudaFree(h->counter); cudaFree(h->tags);
   cudaFree(h->d_in); cudaFree(h->d_out);
   if (h->h_in) cudaFreeHost(h->h_in);
   if (h->h_out) cudaFreeHost(h->h_out);
@@ -612,12 +478,11 @@ int cudampc_solve_batch(cudampc_handle* h, int batch, const double* x0_dev, cons
   BatchArgs a;
   a.x0 = x0_dev; a.ref = ref_dev; a.u_prev = u_prev_dev; a.warm = h->warm; a.scratch = h->scratch;
   a.u0 = u0_dev; a.Xp = Xp_dev; a.Up = Up_dev; a.status = status_dev; a.iters = iters_dev;
-  a.pri = pri_res_dev; a.dua = dua_res_dev; a.info = info_dev; a.counter = h->counter; a.batch = batch;
+  a.pri = pri_res_dev; a.dua = dua_res_dev; a.info = info_dev; a.counter = h->counter; a.batch = batch; a.tags = h->tags;
   int grid = (batch + h->grp_P - 1) / h->grp_P;
   if (grid > h->sms) grid = h->sms;
   const int threads = 32 * h->grp_wpp * h->grp_P;
-  if (h->grp_wpp == 2) mpc_solve_kernel<128, 2><<<grid, threads, h->grp_smem, st>>>(h->p, s, a, h->grp_P, footprint(h->N));
-  else mpc_solve_kernel<256, 1><<<grid, threads, h->grp_smem, st>>>(h->p, s, a, h->grp_P, footprint(h->N));
+  solve_launch(h->variant, grid, threads, h->grp_smem, st, h->p, s, a, h->grp_P, footprint(h->N));
   h->launches++;
   CU(h, cudaGetLastError());
   return CUDAMPC_OK;
@@ -736,19 +601,19 @@ int cudampc_rollout_batch(cudampc_handle* h, int batch, const double* ref_global
   {
     int grid = h->sms * h->roll_per_sm;
     if (grid > batch) grid = batch;
-    mpc_rollout_kernel<<<grid, 32, h->smem_bytes, st>>>(h->p, s, c, a);
+    rollout_launch(grid, h->smem_bytes, st, h->p, s, c, a);
   }
   h->launches++;
   CU(h, cudaGetLastError());
   return CUDAMPC_OK;
 }
 
-#ifdef MPC_TIMING
-int cudampc_debug_tag_cycles(unsigned long long* out16, int reset) {
-  if (cudaMemcpyFromSymbol(out16, g_tag_cycles, sizeof(unsigned long long) * 16) != cudaSuccess) return CUDAMPC_ERR_CUDA;
-  if (reset) { unsigned long long z[16] = {0}; if (cudaMemcpyToSymbol(g_tag_cycles, z, sizeof z) != cudaSuccess) return CUDAMPC_ERR_CUDA; }
+// dev tool (tools/tag_times.py, libraries built with -DMPC_TIMING): cycles between the driver's tags, summed over a launch
+int cudampc_debug_tag_cycles(cudampc_handle* h, unsigned long long* out32, int reset) {
+  if (!h || !h->tags) return CUDAMPC_ERR_INVALID;
+  if (cudaMemcpy(out32, h->tags, sizeof(unsigned long long) * 32, cudaMemcpyDeviceToHost) != cudaSuccess) return CUDAMPC_ERR_CUDA;
+  if (reset && cudaMemset(h->tags, 0, sizeof(unsigned long long) * 32) != cudaSuccess) return CUDAMPC_ERR_CUDA;
   return CUDAMPC_OK;
 }
-#endif
 
 }  // extern "C"

@@ -146,9 +146,6 @@ __device__ __forceinline__ int next_problem_warp(int* counter, int lane) {
 // sweeps / factorisation run in two lanes of ONE warp of the group, chosen so that the chain warps of the resident
 // groups spread over the four SM sub-partitions (warp w issues on sub-partition w % 4).
 // ------------------------------------------------------------------------------------------------
-#ifdef MPC_TIMING
-__device__ unsigned long long g_tag_cycles[16];
-#endif
 struct GroupShared {
   int next;
   int anyv[2];
@@ -169,10 +166,10 @@ struct GroupExec {
     else asm volatile("bar.sync %0, %1;" ::"r"(1 + grp()), "r"(32 * WPP) : "memory");
   }
 #ifdef MPC_TIMING     // dev builds only (tools/tag_times.py): cycles between consecutive tags, summed per tag over the launch
-  long long t_last = 0; int t_cur = 0;
+  long long t_last = 0; int t_cur = 0; unsigned long long* tags = nullptr;
   __device__ __forceinline__ void tag(int n) {
     const long long now = clock64();
-    if (gl() == 0 && t_last) atomicAdd(&g_tag_cycles[t_cur], (unsigned long long)(now - t_last));
+    if (gl() == 0 && t_last && tags) atomicAdd(&tags[t_cur], (unsigned long long)(now - t_last));
     t_last = now; t_cur = n;
   }
 #else

@@ -1,0 +1,176 @@
+// mpc_kernels.cuh — the two heavy kernels of libcudampc.so (K_solve, K_rollout) as templates, and the launch interface of
+// their instantiations.  Every instantiation lives in its own translation unit (mpc_kernels_tu.cu compiled with
+// -DMPC_TU=n) so that the library builds in parallel; cudampc.cu (C ABI + the small kernels) only sees the launchers.
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/cudampc.h"
+#include "mpc_exec.cuh"
+
+using namespace mpc;
+
+struct BatchArgs {
+  const double* x0; const double* ref; const double* u_prev;
+  double* warm; double* scratch;
+  double* u0; double* Xp; double* Up; int* status; int* iters; double* pri; double* dua; int* info;
+  int* counter;
+  int batch;
+  unsigned long long* tags;    // dev builds only (MPC_TIMING)
+};
+
+// ------------------------------------------------------------------------------------------------
+// K_solve: batched MPCController.solve.  The CTA holds P problems, each owned by a group of WPP warps (GroupExec).
+// <256,1>: P <= 8 one-warp groups, 255 registers; <128,2>: P <= 2 two-warp groups for long horizons.
+// ------------------------------------------------------------------------------------------------
+template <int MAXT, int WPP>
+__global__ void __launch_bounds__(MAXT, 1) mpc_solve_kernel(Params p, Settings s, BatchArgs a, int P, int F) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int N = p.N;
+  GroupShared* sh = reinterpret_cast<GroupShared*>(smem + (size_t)P * F) + warp / WPP;
+  int fpad, xpad; layout_pads(N, fpad, xpad);
+  View w{smem + (size_t)(warp / WPP) * F, N, fpad, xpad};
+  GroupExec<WPP> ex{lane, warp, sh};
+#ifdef MPC_TIMING
+  ex.tags = a.tags;
+#endif
+  const int ws = warm_size(N);
+  for (int b = ex.fetch(a.counter); b < a.batch; b = ex.fetch(a.counter)) {
+    ProblemIO io;
+    io.x0 = a.x0 + 4 * (size_t)b;
+    io.ref = RefWin{a.ref + (size_t)4 * (N + 1) * b, 0, N + 1, 1.0};
+    io.u_prev = a.u_prev ? a.u_prev + 2 * (size_t)b : nullptr;
+    io.warm = a.warm + (size_t)ws * b;
+    io.scratch = a.scratch + (size_t)ws * b;
+    io.u0 = a.u0 + 2 * (size_t)b;
+    io.Xp = a.Xp + (size_t)4 * (N + 1) * b;
+    io.Up = a.Up + (size_t)2 * N * b;
+    io.status = a.status + b; io.iters = a.iters + b;
+    io.pri_res = a.pri ? a.pri + b : nullptr; io.dua_res = a.dua ? a.dua + b : nullptr;
+    io.info = a.info ? a.info + 4 * (size_t)b : nullptr;
+    solve_problem(ex, w, p, s, io);
+    ex.group_sync();
+  }
+}
+
+__device__ __forceinline__ void f_discrete_vals(double dt, double L, const double* x, const double* u, double* out) {
+  // vehicle_model.py:11-21 (beta = 0.0 is added to the yaw there)
+  const double yaw = x[2], v = x[3];
+  out[0] = x[0] + dt * v * cos(yaw + 0.0);
+  out[1] = x[1] + dt * v * sin(yaw + 0.0);
+  out[2] = yaw + dt * (v / L) * tan(u[1]);
+  out[3] = v + dt * u[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_rollout: TrajectoryTracker.track for a batch of vehicles, all steps on the device
+// ------------------------------------------------------------------------------------------------
+struct RolloutArgs {
+  const double* ref_global; const int* ref_len; int ref_stride;
+  const double* state0; const double* goal;
+  double* warm; double* scratch; double* work;   // work: per vehicle 16 doubles (state, u_prev, u0 out) + Xp/Up scratch
+  double* states; double* controls; int* n_steps; int* flags; int* step_status; int* step_iters;
+  int* counter; int batch;
+};
+
+__device__ __forceinline__ void f_discrete_dev(const Params& p, const double* x, const double* u, double* out) {
+  f_discrete_vals(p.dt, p.L, x, u, out);
+}
+
+// One vehicle, all steps (TrajectoryTracker.track loop body, control_stage.py:100-150), generic in the execution policy
+template <class Exec>
+__device__ __forceinline__ void rollout_vehicle(Exec& ex, const View& w, const Params& p, const Settings& s,
+                                                const cudampc_rollout_cfg& cfg, const RolloutArgs& a, int b) {
+  const int N = p.N;
+  const int ws = warm_size(N);
+  const int wk = 16 + 4 * (N + 1) + 2 * N;   // per-vehicle global scratch
+  const double nan_ = __longlong_as_double(0x7ff8000000000000LL);
+  double* wkb = a.work + (size_t)wk * b;     // [0..3] state, [4..5] u_prev, [6..7] u0, [10..11] status/iters (int), 16.. Xp, Up
+  const double* refg = a.ref_global + (size_t)4 * a.ref_stride * b;
+  const int len = a.ref_len[b];
+  if (len < 1) {                                           // control_stage.py:71-72 raises for an empty path; per vehicle: aborted, no steps
+    const int T0 = cfg.sim_steps;
+    ex.stages(T0 * 4, [&](int i) { a.states[(size_t)T0 * b * 4 + i] = nan_; });
+    if (a.controls) ex.stages(T0 * 2, [&](int i) { a.controls[(size_t)T0 * b * 2 + i] = nan_; });
+    if (a.step_status) ex.stages(T0, [&](int i) { a.step_status[(size_t)T0 * b + i] = 0; });
+    if (a.step_iters) ex.stages(T0, [&](int i) { a.step_iters[(size_t)T0 * b + i] = 0; });
+    ex.single([&]() { a.n_steps[b] = 0; a.flags[b] = 2; });
+    return;
+  }
+  ex.single([&]() {
+    for (int i = 0; i < 4; ++i) wkb[i] = a.state0[4 * (size_t)b + i];
+    wkb[4] = 0.0; wkb[5] = 0.0;
+  });
+  int path_idx = 0, flags = 0, nst = 0;
+  for (int step = 0; step < cfg.sim_steps; ++step) {
+    int* st_out = a.step_status ? a.step_status + (size_t)cfg.sim_steps * b + step : reinterpret_cast<int*>(wkb + 10);
+    int* it_out = a.step_iters ? a.step_iters + (size_t)cfg.sim_steps * b + step : reinterpret_cast<int*>(wkb + 10) + 1;
+    ProblemIO io;
+    io.x0 = wkb; io.u_prev = wkb + 4;
+    io.ref = RefWin{refg, path_idx, len, 1.0};
+    io.warm = a.warm + (size_t)ws * b; io.scratch = a.scratch + (size_t)ws * b;
+    io.u0 = wkb + 6; io.Xp = wkb + 16; io.Up = wkb + 16 + 4 * (N + 1);
+    io.status = st_out; io.iters = it_out; io.pri_res = nullptr; io.dua_res = nullptr; io.info = nullptr;
+    Settings ss = s;
+    ss.warm_start = (s.warm_start && step > 0) ? 1 : 0;
+    solve_problem(ex, w, p, ss, io);
+    ex.group_sync();
+    int status = *st_out;
+    if (status != STATUS_SOLVED && status != STATUS_SOLVED_INACCURATE && cfg.relax_on_failure) {
+      // control_stage.py:45-56: v_ref *= 0.6, du_bounds widened, one cold retry
+      Params pr = p;
+      pr.du_lo[0] -= cfg.relax_da; pr.du_hi[0] += cfg.relax_da;
+      pr.du_lo[1] -= cfg.relax_ddelta; pr.du_hi[1] += cfg.relax_ddelta;
+      io.ref.vscale = cfg.relax_v_scale;
+      ss.warm_start = 0;
+      solve_problem(ex, w, pr, ss, io);
+      ex.group_sync();
+      status = *st_out;
+      flags |= 4;
+    }
+    if (status != STATUS_SOLVED && status != STATUS_SOLVED_INACCURATE) { flags |= 2; break; }
+    // integrate, carry u_prev, path index rule, goal test (control_stage.py:127-150)
+    double xn[4];
+    f_discrete_dev(p, wkb, wkb + 6, xn);
+    const double u0a = wkb[6], u0d = wkb[7];
+    ex.group_sync();
+    ex.single([&]() {
+      for (int i = 0; i < 4; ++i) { wkb[i] = xn[i]; a.states[((size_t)cfg.sim_steps * b + step) * 4 + i] = xn[i]; }
+      wkb[4] = u0a; wkb[5] = u0d;
+      if (a.controls) { a.controls[((size_t)cfg.sim_steps * b + step) * 2] = u0a; a.controls[((size_t)cfg.sim_steps * b + step) * 2 + 1] = u0d; }
+    });
+    nst = step + 1;
+    if (path_idx < len - 2) {
+      double dx = xn[0] - refg[4 * (size_t)path_idx], dy = xn[1] - refg[4 * (size_t)path_idx + 1];
+      if (dx * dx + dy * dy > cfg.advance_dist2) path_idx += 1;
+    }
+    if (hypot(xn[0] - a.goal[2 * (size_t)b], xn[1] - a.goal[2 * (size_t)b + 1]) < cfg.goal_radius) { flags |= 1; break; }
+  }
+  // rows after the vehicle stopped
+  const int T = cfg.sim_steps, skip = nst + ((flags & 2) ? 1 : 0);
+  ex.stages(T * 4, [&](int i) { if (i >= nst * 4) a.states[(size_t)T * b * 4 + i] = nan_; });
+  if (a.controls) ex.stages(T * 2, [&](int i) { if (i >= nst * 2) a.controls[(size_t)T * b * 2 + i] = nan_; });
+  if (a.step_status) ex.stages(T, [&](int i) { if (i >= skip) a.step_status[(size_t)T * b + i] = 0; });
+  if (a.step_iters) ex.stages(T, [&](int i) { if (i >= skip) a.step_iters[(size_t)T * b + i] = 0; });
+  ex.single([&]() { a.n_steps[b] = nst; a.flags[b] = flags; });
+}
+
+template <int ONE_WARP>      // (a template only so that the kernel is emitted by the one translation unit that launches it)
+__global__ void __launch_bounds__(32) mpc_rollout_kernel(Params p, Settings s, cudampc_rollout_cfg cfg, RolloutArgs a) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31;
+  int fpad, xpad; layout_pads(p.N, fpad, xpad);
+  View w{smem, p.N, fpad, xpad};
+  GroupExec<1> ex{lane, 0, nullptr};
+  for (int b = ex.fetch(a.counter); b < a.batch; b = ex.fetch(a.counter)) rollout_vehicle(ex, w, p, s, cfg, a, b);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Instantiations and their launchers
+// ------------------------------------------------------------------------------------------------
+enum SolveVariant { SOLVE_W1 = 0, SOLVE_W2 = 1 };
+cudaError_t solve_set_smem(int variant, int bytes);
+void solve_launch(int variant, int grid, int threads, int smem, cudaStream_t st, const Params& p, const Settings& s, const BatchArgs& a, int P, int F);
+cudaError_t rollout_set_smem(int bytes);
+cudaError_t rollout_occupancy(int bytes, int* blocks_per_sm);
+void rollout_launch(int grid, int smem, cudaStream_t st, const Params& p, const Settings& s, const cudampc_rollout_cfg& cfg, const RolloutArgs& a);

@@ -162,27 +162,8 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
   // NOTE: every multi-statement lambda above has exactly ONE call site below, so that it is inlined and the solver
   // state it captures stays in registers (a second call site makes nvcc outline it and spill the captures to local memory).
   bool finished = false, need_restore = false;
-  while (!finished) {
-    if (need_factor) {
-      mode = admm_mode(rho, s);
-      ex.tag(5); ex.oe_factor(w, p, mode, oe); ++n_fac;
-      ic = iter_const(w, p, s, rho);
-      need_factor = false;
-    }
-    // one ADMM iteration: right-hand side (odd stages, then even), sweeps over the even stages, update (odd, then even)
-    // (the two parities of a phase share ONE copy of the phase's code: the iteration loop has to stay inside the
-    // instruction cache - 32 KB of L1.5 per SM - also when the resident problems are at different places of the solve)
-    ex.tag(6);
-#pragma unroll 1
-    for (int par = 1; par >= 0; --par) ex.stages_par(NS, par, [&](int k) { admm_rhs_stage_oe(w, p, ic, oe, k); });
-    ++it;
-    ex.tag(1);
-    ex.oe_forward(w, oe);
-    ex.stages_par(NS, 0, [&](int k) { oe_diag_stage(w, oe, k); });
-    ex.oe_backward(w, oe); ++n_solve;
-    ex.tag(2);
-#pragma unroll 1
-    for (int par = 1; par >= 0; --par) ex.stages_par(NS, par, [&](int k) { admm_update_stage_oe(w, p, ic, oe, k); });
+  // what follows the update of iteration `it`: termination check, early / final polish, rho adaptation
+  auto after_update = [&]() {
     const bool last = it >= s.max_iter;
     const bool check = last || ((s.check_termination > 0) && (it % s.check_termination == 0));
     const bool adapt = !last && s.adaptive_rho && (s.adaptive_rho_interval > 0) && (it % s.adaptive_rho_interval == 0);
@@ -232,6 +213,31 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
         }
       }
     }
+  };
+  // One ADMM iteration = right-hand side (odd stages, then even), sweeps over the even stages, update (odd, then even).
+  // The two parities of a phase share ONE copy of the phase's code: the iteration loop has to stay inside the instruction
+  // cache (32 KB of L1.5 per SM) also when the resident problems are at different places of the solve.
+  while (!finished) {
+    if (need_factor) {
+      mode = admm_mode(rho, s);
+      ex.tag(5); ex.oe_factor(w, p, mode, oe); ++n_fac;
+      ic = iter_const(w, p, s, rho);
+      need_factor = false;
+    }
+    ex.tag(6);
+#pragma unroll 1
+    for (int par = 1; par >= 0; --par) ex.stages_par(NS, par, [&](int k) { admm_rhs_stage_oe(w, p, ic, oe, k); });
+    ++it;
+    ex.tag(16);
+    ex.oe_forward(w, oe);
+    ex.tag(17);
+    ex.stages_par(NS, 0, [&](int k) { oe_diag_stage(w, oe, k); });
+    ex.tag(18);
+    ex.oe_backward(w, oe); ++n_solve;
+    ex.tag(2);
+#pragma unroll 1
+    for (int par = 1; par >= 0; --par) ex.stages_par(NS, par, [&](int k) { admm_update_stage_oe(w, p, ic, oe, k); });
+    after_update();
   }
   ex.tag(7);
   if (need_restore) restore_iterate(io.warm);   // polish rejected outright: the answer is the ADMM iterate

@@ -6,8 +6,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 dbg = os.path.join(ROOT, "rrt_mpc_b200", "libcudampc_timing.so")
 if "--build" in sys.argv or not os.path.exists(dbg):
-    subprocess.run(["nvcc", "-DMPC_TIMING", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
-                    "-o", dbg, os.path.join(ROOT, "rrt_mpc_b200", "csrc", "cudampc.cu")], check=True)
+    import __graft_entry__ as G
+    G.build_cuda(dbg, extra=["-DMPC_TIMING"], tag="_timing")
     if "--build" in sys.argv: sys.exit(0)
 import rrt_mpc_b200._lib as L
 L.LIB_PATH = dbg
@@ -22,14 +22,14 @@ ctl = MPCController(par, SolverSettings(eps_abs=1e-6, eps_rel=1e-6, polish_passe
 lib = L.load()
 d = lambda a: torch.as_tensor(a).cuda()
 dx0, dref, dup = d(x0), d(ref), d(up)
-out = (C.c_ulonglong * 16)()
+out = (C.c_ulonglong * 32)()
 r = ctl.solve_batch(dx0, dref, u_prev=dup); torch.cuda.synchronize()
-lib.cudampc_debug_tag_cycles(out, 1)
+lib.cudampc_debug_tag_cycles(ctl._handle(1).ptr, out, 1)
 r = ctl.solve_batch(dx0, dref, u_prev=dup); torch.cuda.synchronize()
-lib.cudampc_debug_tag_cycles(out, 1)
-names = ["setup+first factor", "sweeps (ADMM)", "A1 update", "residuals/check", "assemble (rho)", "factor (rho)", "A2 rhs", "final/outputs",
+lib.cudampc_debug_tag_cycles(ctl._handle(1).ptr, out, 1)
+names = ["setup", "-", "update (odd: expand + A1, even: A1)", "residuals/check", "-", "factor (ADMM)", "rhs (odd: A2 + t, even: A2 + b')", "final/outputs",
          "save iterate", "polish: activity+assemble", "polish: factor", "polish: 4x(rhs, solve, dual, primal)", "polish: residuals+decision",
-         "resume: load+assemble", "resume: factor", "early probe"]
+         "resume: load+assemble", "resume: factor", "early probe", "sweep forward + middle", "diagonal step", "sweep backward"] + ["-"] * 13
 v = np.array(list(out), dtype=np.float64); it = r.iters.double().mean().item(); info = r.info.double().mean(0).cpu().numpy()
 print(f"N={N} B={B} early={early}: mean iters {it:.1f}, factorisations {info[1]:.2f}, solves {info[3]:.1f}, total {v.sum()/B/1e3:.0f} k cycles per problem")
 for n, c in sorted(zip(names, v), key=lambda t: -t[1]):
