@@ -4,10 +4,15 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (libcudampc.so)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path, restated (oracle/), all host cores
 
-A "step" is one pass of the hot path over one batch: `batch` independent horizon-50 tracking QPs
-(BASELINE.json configs[2]: 65,536 problems, steering-rate limit +-0.02 rad/step) per GPU.  Under torchrun
-each rank solves its own shard of one seeded global batch (weak scaling, no collective on the data path);
-torch.distributed is used only to gather the per-rank times and counters.  One JSON line on rank 0.
+Headline (`value`, `e2e`, `roofline`): BASELINE.json configs[2] - 65,536 independent horizon-50 tracking QPs with the
+steering-rate limit +-0.02 rad/step PER GPU; a "step" is one pass of the hot path over that batch.  Under torchrun every rank
+solves its own shard of one seeded global batch (weak scaling, no collective on the data path); torch.distributed only gathers
+the per-rank times and counters.  The same JSON line carries a `configs` block with the other BASELINE configurations as the
+driver's default invocation measures them:
+  config2  4,096 x horizon 20 (default limits), L2 flushed between launches                          (rank 0)
+  config4  closed-loop roll-out of 8,192 vehicles x 500 steps, warm start, per-step p50 / p99 latency   (rank 0)
+  config5  the 1,048,576-problem horizon-50 sweep (seed 5) split over the N ranks: STRONG scaling       (all ranks)
+One JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -34,14 +39,15 @@ DU_DELTA = 0.02            # rad/step, configs[2] "tight steering-rate limits"
 EPS = 1e-6                 # parity setting of BASELINE.json (u0 within 1e-5 at eps_abs = eps_rel = 1e-6)
 POLISH_PASSES = 5
 POLISH_RETRY = 4           # with 4, every problem of the bench batch ends on a polished KKT point (2 leaves 1 of 65,536)
-EARLY_POLISH = 1          # finish as soon as a polish certifies a KKT point of a settled active set
+EARLY_POLISH = 1           # finish as soon as a polish certifies a KKT point of a settled active set
+SWEEP_BATCH = 1 << 20      # configs[4]: 1,048,576 problems, seed 5
+FP64_NOMINAL_TFLOPS = 37.2  # B200 data-sheet non-tensor fp64 rate (the live DFMA probe measures ~34)
 
 # canonical flop model of BASELINE.md §2 / SURVEY.md §8d (n = 11N+5, m = 19N+7, nnz(A) = 43N+5)
 _NNZ_L = {15: 706, 20: 941, 50: 2349}
-# DRAM traffic per solve of K_solve from the ncu --set full capture profiles/ncu_full_r01_solve_summary.txt
-# (dram__bytes_read.sum + dram__bytes_write.sum = 8.49 + 56.18 MB for a 4,096-problem launch): dominated by the
-# warm-start / polish back-up of the ADMM iterate (12 KB per save), not by the 4.1 KB of algorithmic I/O.
-TRAFFIC_BYTES_PER_SOLVE = 64.67e6 / 4096
+# DRAM traffic per solve of K_solve: dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture committed under
+# profiles/ (see profiles/README.md for the file and launch it comes from); a constant from that capture, not measured live.
+TRAFFIC_BYTES_PER_SOLVE = None     # filled from profiles/traffic.json when present
 
 
 def flop_model(N: int):
@@ -64,9 +70,11 @@ def io_bytes(N, B):
     return B * (32 * N + 80), B * (48 * N + 56)
 
 
-def shard_range(rank: int, world: int, per_rank: int):
-    """Static contiguous split of the global batch index."""
-    return rank * per_rank, per_rank
+def shard_range(rank: int, world: int, total: int):
+    """Static contiguous split of a global batch of `total` problems over `world` ranks: (start, count)."""
+    base, rem = divmod(total, world)
+    start = rank * base + min(rank, rem)
+    return start, base + (1 if rank < rem else 0)
 
 
 def product_params(N=HORIZON, du=DU_DELTA):
@@ -134,14 +142,16 @@ def _cpu_worker(args):
     x0, ref, up = make_batch(batch, N, seed, start=lo, count=hi - lo)
     CO.lib()
     t = time.perf_counter()
-    r = CO.solve_batch(p, x0, ref, up, eps_abs=eps, eps_rel=eps, scaling=scaling, polish_passes=1)
+    r = CO.solve_batch(p, x0, ref, up, eps_abs=eps, eps_rel=eps, scaling=scaling, polish_passes=1, z0_projected=int(scaling == 0))
     dt = time.perf_counter() - t
     return dt, int((r["status"] == 1).sum()), float(r["iters"].mean())
 
 
 def cpu_baseline(sample: int, N=HORIZON, eps=EPS, scaling=10, cores=None):
     """Cold solves (the reference rebuilds its problem every call, mpc_controller.py:119) of the first `sample`
-    problems of the bench batch with the restated OSQP path at OSQP's default scaling; input generation excluded."""
+    problems of the bench batch with the restated OSQP path; input generation excluded.  scaling = 10: OSQP's default
+    (what the reference runs); scaling = 0: the unscaled iteration the CUDA kernel runs (same algorithm, for the split
+    of the GPU/CPU ratio into hardware and iteration count)."""
     import multiprocessing as mp
     cores = cores or os.cpu_count() or 1
     per = max(1, sample // cores)
@@ -181,6 +191,111 @@ def run_reference(args, rank, world):
 
 
 # ----------------------------------------------------------------------------------------------------
+# The other BASELINE configurations
+# ----------------------------------------------------------------------------------------------------
+def timed_launches(torch, dev, stream, flush, fn, reps):
+    """CUDA-event time of `reps` launches of fn() with an L2 flush (untimed) before each."""
+    out = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream); res = fn(); e1.record(stream)
+        torch.cuda.synchronize(dev)
+        out.append(e0.elapsed_time(e1))
+    return np.array(out), res
+
+
+def run_config2(torch, dev, stream, flush, local_rank, peak_tf, reps=30):
+    """BASELINE configs[1]: 4,096 independent QPs, horizon 20, default limits, one launch (7 MB of I/O: L2 flushed)."""
+    from rrt_mpc_b200 import MPCController, SolverSettings
+    from rrt_mpc_b200.synthetic import make_batch
+    N, B = 20, 4096
+    x0, ref, up = make_batch(B, N, 2)
+    d = [torch.as_tensor(a).to(dev) for a in (x0, ref, up)]
+    out = {"workload": "4,096 independent tracking QPs, horizon 20, default limits (BASELINE.json configs[1]), seed 2; one launch, "
+                       "256 MB written between launches to flush L2", "batch": B, "horizon": N}
+    for name, early in (("early_polish", True), ("osqp_literal", False)):
+        ctl = MPCController(product_params(N, 0.15), SolverSettings(eps_abs=EPS, eps_rel=EPS, polish_passes=POLISH_PASSES, polish_retry=POLISH_RETRY,
+                                                                      early_polish=early), device=local_rank, max_batch=B)
+        for _ in range(3):
+            ctl.solve_batch(d[0], d[1], u_prev=d[2])
+        ms, res = timed_launches(torch, dev, stream, flush, lambda: ctl.solve_batch(d[0], d[1], u_prev=d[2]), reps)
+        it, info = res.iters.cpu().numpy(), res.info.cpu().numpy()
+        tf = flops_of_batch(N, it, info[:, 1], info[:, 3]) / (ms.mean() * 1e-3) / 1e12
+        out[name] = {"value": B / (ms.mean() * 1e-3), "unit": UNIT, "ms_per_step": float(ms.mean()), "p50_ms": float(np.percentile(ms, 50)),
+                     "p99_ms": float(np.percentile(ms, 99)), "launches": reps, "iters_mean": float(it.mean()),
+                     "solved_frac": float((res.status == 1).double().mean().item()), "polished_frac": float((info[:, 2] > 0).mean()),
+                     "problems_per_sm": ctl.problems_per_sm(),
+                     "roofline": {"bound": "fp64", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf if peak_tf > 0 else None}}
+        ctl.close()
+    return out
+
+
+def run_config4(torch, dev, local_rank, vehicles=8192, steps=500):
+    """BASELINE configs[3]: closed-loop roll-out of 8,192 vehicles along perturbed copies of the default RRT* path for 500 steps,
+    per-step relinearisation, warm start, everything on the device (one launch of K_rollout; goals placed out of reach so that
+    every vehicle runs all steps).  Per-step latency: %globaltimer around every closed-loop step of every vehicle."""
+    from rrt_mpc_b200 import MPCConfig, SolverSettings, TrajectoryTracker
+    d = np.load(os.path.join(ROOT, "tests", "golden", "default_scenario.npz"))
+    path = np.array(d["path"])
+    rng = np.random.default_rng(4)
+    noise = rng.normal(size=(vehicles,) + path.shape) * 0.15
+    noise[:, 0] = 0.0
+    paths = [path + noise[b] for b in range(vehicles)]
+    starts = path[0] + rng.normal(size=(vehicles, 2)) * 0.5
+    goals = np.full((vehicles, 2), 1e9)
+    tr = TrajectoryTracker(MPCConfig(sim_steps=steps), None, device=local_rank,
+                           settings=SolverSettings(eps_abs=EPS, eps_rel=EPS, polish_passes=POLISH_PASSES, polish_retry=POLISH_RETRY, early_polish=False))
+    tr.track_batch(paths[:512], starts[:512], goals[:512], map_resolution=0.8, warm_start=True, sim_steps=50)      # warm-up
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t = time.perf_counter()
+    e0.record()
+    res = tr.track_batch(paths, starts, goals, map_resolution=0.8, warm_start=True, record_step_time=True)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - t
+    n = int(res.n_steps.sum())
+    ns = res.step_ns[res.step_status != 0].astype(np.float64)
+    return {"workload": f"{vehicles} vehicles x {steps} closed-loop steps along perturbed copies of the default RRT* path (BASELINE.json configs[3]), "
+                        "horizon 15, warm start, OSQP-literal termination + polish, references built on the device, one K_rollout launch",
+            "vehicles": vehicles, "sim_steps": steps, "vehicle_steps": n, "value": n / wall, "unit": "vehicle-steps/s (= closed-loop MPC solves/s)",
+            "wall_s": wall, "device_ms_incl_reference_build_and_d2h": float(e0.elapsed_time(e1)), "aborted": int(res.aborted.sum()),
+            "relaxed": int(res.relaxed.sum()), "iters_mean_per_step": float(res.step_iters[res.step_status != 0].mean()),
+            "step_latency_us": {"p50": float(np.percentile(ns, 50)) / 1e3, "p99": float(np.percentile(ns, 99)) / 1e3, "max": float(ns.max()) / 1e3,
+                                "mean": float(ns.mean()) / 1e3, "samples": int(ns.size),
+                                "note": "one closed-loop step of one vehicle (window gather, solve, f_discrete, path-index rule) while "
+                                        "all vehicles share the GPU"}}
+
+
+def run_config5(torch, dist, dev, stream, rank, world, local_rank):
+    """BASELINE configs[4]: the 1,048,576-problem horizon-50 sweep (seed 5), split contiguously over the ranks - STRONG scaling.
+    One warm-up and one timed step per rank (device resident); time = max over ranks."""
+    from rrt_mpc_b200 import MPCController, SolverSettings
+    from rrt_mpc_b200.synthetic import make_batch
+    start, count = shard_range(rank, world, SWEEP_BATCH)
+    x0, ref, up = make_batch(SWEEP_BATCH, HORIZON, 5, start=start, count=count)
+    ctl = MPCController(product_params(), SolverSettings(eps_abs=EPS, eps_rel=EPS, polish_passes=POLISH_PASSES, polish_retry=POLISH_RETRY,
+                                                         early_polish=bool(EARLY_POLISH)), device=local_rank, max_batch=count)
+    d = [torch.as_tensor(a).to(dev) for a in (x0, ref, up)]
+    ctl.solve_batch(d[0][:BATCH], d[1][:BATCH], u_prev=d[2][:BATCH])
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream); res = ctl.solve_batch(d[0], d[1], u_prev=d[2]); e1.record(stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    info = res.info.cpu().numpy()
+    local = {"ms": ms, "count": float(count), "solved": float((res.status == 1).sum().item()), "polished": float((info[:, 2] > 0).sum()),
+             "iters": float(res.iters.double().sum().item())}
+    ctl.close()
+    return local
+
+
+# ----------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -191,6 +306,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=2048, help="problems in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--latency-launches", type=int, default=100, help="launches of one resident wave for the latency percentiles")
+    ap.add_argument("--skip-configs", action="store_true", help="headline only: skip the config2 / config4 / config5 blocks")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -217,7 +333,7 @@ def main():
     warmup = max(3, args.warmup)
     params = product_params()
     settings = SolverSettings(eps_abs=EPS, eps_rel=EPS, polish_passes=POLISH_PASSES, polish_retry=POLISH_RETRY, early_polish=bool(EARLY_POLISH))
-    start, count = shard_range(rank, world, B)
+    start, count = rank * B, B                      # weak scaling: every rank its own B problems of the seeded global batch
     x0, ref, up = make_batch(B * world, N, SEED, start=start, count=count)
     ctl = MPCController(params, settings, device=local_rank, max_batch=B)
     dev = torch.device("cuda", local_rank)
@@ -263,17 +379,20 @@ def main():
     lit = SolverSettings(eps_abs=EPS, eps_rel=EPS, polish_passes=POLISH_PASSES, polish_retry=POLISH_RETRY, early_polish=False)
     ctl.solve_batch(d_x0, d_ref, u_prev=d_up, settings=lit)
     sync()
-    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    flush.zero_()
-    l0.record(stream); lres = ctl.solve_batch(d_x0, d_ref, u_prev=d_up, settings=lit); l1.record(stream)
-    sync()
-    lit_ms = l0.elapsed_time(l1)
+    lit_ms = []
+    for _ in range(max(2, min(args.steps, 3))):
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.zero_()
+        l0.record(stream); lres = ctl.solve_batch(d_x0, d_ref, u_prev=d_up, settings=lit); l1.record(stream)
+        sync()
+        lit_ms.append(l0.elapsed_time(l1))
+    lit_ms = float(np.mean(lit_ms))
     lit_iters = lres.iters.cpu().numpy(); lit_info = lres.info.cpu().numpy()
     lit_flops = flops_of_batch(N, lit_iters, lit_info[:, 1], lit_info[:, 3])
     u0_gap = float((lres.u0 - res.u0).abs().max().item())
 
     # ---- per-launch latency of one resident wave (BASELINE metric: p99 per-step latency) -----------------------------
-    wave = min(B, 148 * ctl.problems_per_sm())
+    wave = min(B, 148 * ctl.problems_per_sm())          # (SMs x problems/SM)
     lat = []
     for i in range(args.latency_launches):
         o = (i * wave) % max(1, B - wave + 1)
@@ -283,13 +402,13 @@ def main():
         lat.append(a0.elapsed_time(a1))
     lat = np.array(lat[5:]) if len(lat) > 10 else np.array(lat)
 
-    # ---- end-to-end through the public API with host buffers ---------------------------------------
+    # ---- end-to-end through the public API with host buffers, EVERY step timed ------------------------------------------
     ctl.pinned_outputs = True            # page-locked result arrays, reused per call (inputs are pinned above)
-    for _ in range(1):
+    for _ in range(2):
         ctl.solve_batch(h_x0, h_ref, u_prev=h_up)
     sync()
     e2e_t = []
-    for _ in range(max(2, min(args.steps, 3))):
+    for _ in range(args.steps):
         t = time.perf_counter()
         hres = ctl.solve_batch(h_x0, h_ref, u_prev=h_up)
         e2e_t.append(time.perf_counter() - t)
@@ -297,22 +416,45 @@ def main():
     h2d = B * (4 + 4 * (N + 1) + 2) * 8
     d2h = B * (2 + 4 * (N + 1) + 2 * N + 2) * 8 + B * 6 * 4
     assert np.array_equal(hres.status, status)
+    per_sm, ws_doubles = ctl.problems_per_sm(), ctl.workspace_doubles()
+    ctl.close()
 
     local = {"ms_total": float(np.sum(step_ms)), "ms_max_step": float(np.max(step_ms)), "solves": float(B * args.steps), "flops": flops,
              "solved": float((status == 1).sum()), "iters_mean": float(iters.mean()), "iters_max": float(iters.max()),
-             "e2e_s": float(np.mean(e2e_t)), "launches": float(launches), "polished": float((info[:, 2] > 0).sum()),
-             "n_fac_mean": float(info[:, 1].mean()), "wall_s": t_wall, "lit_ms": lit_ms, "lit_solves": float(B)}
+             "e2e_total_s": float(np.sum(e2e_t)), "e2e_max_s": float(np.max(e2e_t)), "launches": float(launches), "polished": float((info[:, 2] > 0).sum()),
+             "n_fac_mean": float(info[:, 1].mean()), "wall_s": t_wall, "lit_ms": lit_ms, "lit_solves": float(B),
+             "lit_polished": float((lit_info[:, 2] > 0).sum())}
     allm = gather_metrics(local, world)
+
+    # ---- the other BASELINE configurations ------------------------------------------------------------------------------
+    configs = {}
+    c5 = None
+    if not args.skip_configs:
+        del d_x0, d_ref, d_up
+        torch.cuda.empty_cache()
+        c5 = gather_metrics(run_config5(torch, dist, dev, stream, rank, world, local_rank), world)
+        if rank == 0:
+            configs["config2"] = run_config2(torch, dev, stream, flush, local_rank, peak_tf)
+            configs["config4"] = run_config4(torch, dev, local_rank)
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
+    if c5 is not None:
+        t5 = max(m["ms"] for m in c5) * 1e-3
+        n5 = sum(m["count"] for m in c5)
+        configs["config5"] = {"workload": f"{SWEEP_BATCH} independent tracking QPs, horizon {HORIZON}, steering-rate +-{DU_DELTA}, seed 5 (BASELINE.json configs[4]), "
+                                          f"split contiguously over {world} GPU(s), device resident, one timed step, time = max over ranks",
+                              "scaling": "strong", "global_batch": int(n5), "n_gpus": world, "ms_per_step": t5 * 1e3, "value": n5 / t5, "unit": UNIT,
+                              "solved_frac": sum(m["solved"] for m in c5) / n5, "polished_frac": sum(m["polished"] for m in c5) / n5,
+                              "iters_mean": sum(m["iters"] for m in c5) / n5, "per_rank_ms": [m["ms"] for m in c5]}
 
     t_ms = max(m["ms_total"] for m in allm)                     # max over ranks
     total_solves = sum(m["solves"] for m in allm)
     value = total_solves / (t_ms * 1e-3)
     ms_per_step = t_ms / args.steps
-    e2e_value = (B * world) / max(m["e2e_s"] for m in allm)
+    e2e_value = (B * world * args.steps) / max(m["e2e_total_s"] for m in allm)
     # roofline of the dominant (only) kernel, per launch on rank 0: canonical flops / CUDA-event duration
     ach_tf = flops / (float(np.mean(step_ms)) * 1e-3) / 1e12
     inb, outb = io_bytes(N, B)
@@ -321,39 +463,60 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_ach = (inb + outb) / (float(np.mean(step_ms)) * 1e-3) / 1e9
-    cb = None
+    cb = cb0 = None
     if not args.no_cpu_baseline:
         cb = cpu_baseline(args.cpu_sample)
+        cb0 = cpu_baseline(max(args.cpu_sample // 2, os.cpu_count() or 1), scaling=0)
+        cb["same_algorithm"] = {"value": cb0["value"], "unit": UNIT, "mean_iters": cb0["mean_iters"], "sample": cb0["sample"],
+                                "note": "the C port run as the kernel runs OSQP (scaling 0, z0 = clip(0)): compare with value_literal - "
+                                        "that ratio is hardware + implementation; the rest of the headline ratio is iteration count"}
+    lit_value = sum(m["lit_solves"] for m in allm) / (max(m["lit_ms"] for m in allm) * 1e-3)
+    lit_tf = lit_flops / (lit_ms * 1e-3) / 1e12
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
         "ms_per_step": ms_per_step, "p99_ms_per_step": float(np.percentile(step_ms, 99)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "value_literal": lit_value,
         "config": {"workload": f"{B} independent tracking QPs per GPU, horizon {N}, 4 states / 2 controls, steering-rate +-{DU_DELTA} rad/step "
                                f"(BASELINE.json configs[2]), seed {SEED}", "batch_per_gpu": B, "horizon": N, "eps_abs": EPS, "eps_rel": EPS,
                    "polish_passes": POLISH_PASSES, "polish_retry": POLISH_RETRY, "early_polish": EARLY_POLISH, "parallelism": f"{world} x independent shards, no data-path collective",
+                   "termination": "value: early certified polish (finishes as soon as a polish ends on a KKT point of a settled active set); "
+                                  "value_literal: the same kernel with OSQP's own termination (residual test at eps 1e-6, then polish)",
                    "l2": "working set per step (inputs 112 MB + outputs 161 MB + 803 MB warm-start state) exceeds the 126 MB L2; "
                          "a 256 MB write flushes L2 between timed steps"},
         "solve_stats": {"solved_frac": sum(m["solved"] for m in allm) / (B * world), "iters_mean": float(np.mean([m["iters_mean"] for m in allm])),
                         "iters_max": max(m["iters_max"] for m in allm), "polished_frac": sum(m["polished"] for m in allm) / (B * world),
                         "factorisations_mean": float(np.mean([m["n_fac_mean"] for m in allm])),
-                        "problems_per_sm": ctl.problems_per_sm(), "smem_doubles_per_problem": ctl.workspace_doubles()},
-        "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf > 0 else None,
-                     "traffic": TRAFFIC_BYTES_PER_SOLVE * B, "traffic_unit": "bytes per launch (ncu r01, scaled per solve)",
+                        "problems_per_sm": per_sm, "smem_doubles_per_problem": ws_doubles},
+        "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "peak_nominal": FP64_NOMINAL_TFLOPS, "unit": "TFLOP/s",
+                     "frac": ach_tf / peak_tf if peak_tf > 0 else None, "frac_of_nominal": ach_tf / FP64_NOMINAL_TFLOPS,
+                     "traffic": (traffic["bytes_per_solve"] * B) if traffic else None,
+                     "traffic_unit": "bytes per launch" + (f" ({traffic['source']})" if traffic else ""),
                      "note": "binding roofline is the non-tensor fp64 pipe (SURVEY.md 8d); achieved = canonical flops (BASELINE.md model, from the "
                              "kernel's own iteration/factorisation counters) / CUDA-event time of one launch; peak = DFMA throughput measured "
-                             "live by cudampc_fp64_peak_tflops (MEASURED_PEAKS.json has no fp64 figure)",
+                             "live by cudampc_fp64_peak_tflops (MEASURED_PEAKS.json has no fp64 figure), peak_nominal = data sheet",
                      "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                              "algorithmic_bytes_per_launch": inb + outb, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
-        "osqp_literal": {"value": sum(m["lit_solves"] for m in allm) / (max(m["lit_ms"] for m in allm) * 1e-3), "unit": UNIT,
-                         "iters_mean": float(lit_iters.mean()), "achieved_tflops": lit_flops / (lit_ms * 1e-3) / 1e12,
-                         "frac": lit_flops / (lit_ms * 1e-3) / 1e12 / peak_tf if peak_tf > 0 else None, "max_abs_u0_gap_vs_early_polish": u0_gap,
+        "osqp_literal": {"value": lit_value, "unit": UNIT, "ms_per_step": lit_ms,
+                         "iters_mean": float(lit_iters.mean()), "achieved_tflops": lit_tf,
+                         "frac": lit_tf / peak_tf if peak_tf > 0 else None, "frac_of_nominal": lit_tf / FP64_NOMINAL_TFLOPS,
+                         "polished_frac": sum(m["lit_polished"] for m in allm) / (B * world), "max_abs_u0_gap_vs_early_polish": u0_gap,
                          "note": "same kernel with early_polish off: ADMM runs until the eps 1e-6 residual test passes, then polishes"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps_timed": args.steps,
+                "ms_per_step_mean": 1e3 * float(np.mean(e2e_t)), "ms_per_step_p99": 1e3 * float(np.percentile(e2e_t, 99)),
+                "ms_per_step_max_over_ranks": 1e3 * max(m["e2e_max_s"] for m in allm),
+                "note": "MPCController.solve_batch on pinned host arrays: H2D, solve, D2H inside every timed call"},
         "latency": {"batch": int(wave), "launches": int(len(lat)), "p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
                     "note": "one launch of exactly one resident wave of problems (SMs x problems/SM), device-resident, rank 0"},
+        "configs": configs,
         "gpu_launches": int(sum(m["launches"] for m in allm)),
         "clocks": clk,
         "cpu_baseline": cb,
@@ -361,6 +524,7 @@ def main():
     }
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -101,6 +101,9 @@ typedef struct cudampc_rollout_cfg {
   double relax_v_scale;     /* 0.6 */
   double relax_da;          /* 5.0 */
   double relax_ddelta;      /* 0.05 */
+  int32_t* step_ns_dev;     /* optional device array (B, sim_steps) int32: wall time of every closed-loop step of every vehicle
+                               in nanoseconds (%globaltimer around window gather + solve (+ retry) + f_discrete + path-index
+                               rule), 0 for steps not run; NULL = not recorded.  What "p99 per-step latency" is measured from. */
 } cudampc_rollout_cfg;
 
 typedef struct cudampc_handle cudampc_handle;

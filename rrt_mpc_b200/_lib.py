@@ -29,7 +29,7 @@ class Settings(C.Structure):
 class RolloutCfg(C.Structure):
     _fields_ = [("sim_steps", C.c_int32), ("relax_on_failure", C.c_int32), ("advance_dist2", C.c_double),
                 ("goal_radius", C.c_double), ("relax_v_scale", C.c_double), ("relax_da", C.c_double),
-                ("relax_ddelta", C.c_double)]
+                ("relax_ddelta", C.c_double), ("step_ns_dev", C.c_void_p)]
 
 
 # every symbol include/cudampc.h declares (tests/test_abi.py checks the library exports all of them)

@@ -46,6 +46,7 @@ class BatchTrackingResult:
     step_status: np.ndarray   # (B, T) int32 OSQP codes (0 = not run)
     step_iters: np.ndarray    # (B, T) int32
     relaxed: Optional[np.ndarray] = None   # (B,) bool: the relaxation retry (control_stage.py:45-56) ran at least once
+    step_ns: Optional[np.ndarray] = None   # (B, T) int32: wall time of every closed-loop step on the device (ns), if recorded
 
     def result(self, b: int) -> TrackingResult:
         return TrackingResult(states=[self.states[b, t].copy() for t in range(int(self.n_steps[b]))])
@@ -148,7 +149,7 @@ class TrajectoryTracker:
     # -- batched, device-resident closed loop ---------------------------------------------------------
     def track_batch(self, paths: Sequence, starts, goals, *, map_resolution: float, sim_steps: Optional[int] = None,
                     ref_globals: Optional[Sequence[np.ndarray]] = None, states0=None, warm_start: bool = True,
-                    relax_on_failure: bool = True, build_on_device: bool = True) -> BatchTrackingResult:
+                    relax_on_failure: bool = True, build_on_device: bool = True, record_step_time: bool = False) -> BatchTrackingResult:
         """Track ``B`` vehicles. ``paths[b]`` is a polyline (as ``PlanResult.path``); ``starts``/``goals`` are
         ``(B,2)``.  Alternatively pass prebuilt ``ref_globals`` (each ``(M_b,4)``) and ``states0 (B,4)``."""
         import torch
@@ -193,6 +194,8 @@ class TrajectoryTracker:
         cfg = _lib.RolloutCfg()
         h.lib.cudampc_default_rollout_cfg(C.byref(cfg))
         cfg.sim_steps, cfg.relax_on_failure = T, int(relax_on_failure)
+        d_ns = torch.zeros((B, T), dtype=torch.int32, device=dev) if record_step_time else None
+        cfg.step_ns_dev = d_ns.data_ptr() if d_ns is not None else None
         p = lambda x: C.c_void_p(x.data_ptr())
         rc = h.lib.cudampc_rollout_batch(h.ptr, B, p(d_ref), p(d_len), stride, p(d_s0), p(d_goal), C.byref(s), C.byref(cfg),
                                          p(d_states), p(d_ctrl), p(d_n), p(d_fl), p(d_st), p(d_it),
@@ -202,7 +205,8 @@ class TrajectoryTracker:
         flags = d_fl.cpu().numpy()
         return BatchTrackingResult(states=d_states.cpu().numpy(), controls=d_ctrl.cpu().numpy(), n_steps=d_n.cpu().numpy(),
                                    goal_reached=(flags & 1).astype(bool), aborted=(flags & 2).astype(bool),
-                                   step_status=d_st.cpu().numpy(), step_iters=d_it.cpu().numpy(), relaxed=(flags & 4).astype(bool))
+                                   step_status=d_st.cpu().numpy(), step_iters=d_it.cpu().numpy(), relaxed=(flags & 4).astype(bool),
+                                   step_ns=d_ns.cpu().numpy() if d_ns is not None else None)
 
 
 def _reference_plotter():

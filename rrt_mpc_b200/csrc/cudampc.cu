@@ -172,6 +172,7 @@ struct cudampc_handle {
   int sms, smem_bytes, roll_per_sm;   // K_rollout: one-warp CTAs of smem_bytes each, roll_per_sm resident per SM
   int grp_P, grp_wpp, grp_smem;        // K_solve: one CTA per SM with grp_P groups of grp_wpp warps
   int variant;                         // SolveVariant
+  bool short_form;                     // N+1 <= 32: short form of the ADMM phases (K_solve one-warp groups, K_rollout)
   unsigned long long* tags;            // dev builds (MPC_TIMING): per-tag cycle counters
   long long launches;
   char err[512];
@@ -180,12 +181,23 @@ struct cudampc_handle {
 static char g_create_err[512] = "";
 
 // launchers of the kernel instantiations (mpc_kernels_tu.cu, one translation unit each)
-cudaError_t solve_set_smem_0(int), solve_set_smem_1(int);
+cudaError_t solve_set_smem_0(int), solve_set_smem_1(int), solve_set_smem_2(int);
 void solve_launch_0(int, int, int, cudaStream_t, const Params&, const Settings&, const BatchArgs&, int, int);
 void solve_launch_1(int, int, int, cudaStream_t, const Params&, const Settings&, const BatchArgs&, int, int);
-cudaError_t solve_set_smem(int v, int bytes) { return v == SOLVE_W1 ? solve_set_smem_0(bytes) : solve_set_smem_1(bytes); }
+void solve_launch_2(int, int, int, cudaStream_t, const Params&, const Settings&, const BatchArgs&, int, int);
+cudaError_t rollout_set_smem_short(int), rollout_set_smem_general(int), rollout_occupancy_short(int, int*), rollout_occupancy_general(int, int*);
+void rollout_launch_short(int, int, cudaStream_t, const Params&, const Settings&, const cudampc_rollout_cfg&, const RolloutArgs&);
+void rollout_launch_general(int, int, cudaStream_t, const Params&, const Settings&, const cudampc_rollout_cfg&, const RolloutArgs&);
+cudaError_t solve_set_smem(int v, int bytes) { return v == 0 ? solve_set_smem_0(bytes) : v == 1 ? solve_set_smem_1(bytes) : solve_set_smem_2(bytes); }
 void solve_launch(int v, int grid, int threads, int smem, cudaStream_t st, const Params& p, const Settings& s, const BatchArgs& a, int P, int F) {
-  if (v == SOLVE_W1) solve_launch_0(grid, threads, smem, st, p, s, a, P, F); else solve_launch_1(grid, threads, smem, st, p, s, a, P, F);
+  if (v == 0) solve_launch_0(grid, threads, smem, st, p, s, a, P, F);
+  else if (v == 1) solve_launch_1(grid, threads, smem, st, p, s, a, P, F);
+  else solve_launch_2(grid, threads, smem, st, p, s, a, P, F);
+}
+cudaError_t rollout_set_smem(bool sf, int bytes) { return sf ? rollout_set_smem_short(bytes) : rollout_set_smem_general(bytes); }
+cudaError_t rollout_occupancy(bool sf, int bytes, int* n) { return sf ? rollout_occupancy_short(bytes, n) : rollout_occupancy_general(bytes, n); }
+void rollout_launch(bool sf, int grid, int smem, cudaStream_t st, const Params& p, const Settings& s, const cudampc_rollout_cfg& cfg, const RolloutArgs& a) {
+  if (sf) rollout_launch_short(grid, smem, st, p, s, cfg, a); else rollout_launch_general(grid, smem, st, p, s, cfg, a);
 }
 
 // Every entry point runs on the handle's device and leaves the caller's current device as it found it.
@@ -336,10 +348,12 @@ int cudampc_create(const cudampc_params* params, int max_batch, int device, cuda
   h->smem_bytes = F * (int)sizeof(double);
   const int optin = (int)prop.sharedMemPerBlockOptin;
   if (h->smem_bytes + (int)sizeof(GroupShared) > optin) { delete h; return fail(nullptr, CUDAMPC_ERR_UNSUPPORTED, "%s", "horizon too long for one problem per 227 KB of shared memory"); }
-  // K_rollout: one-warp CTAs
-  e = rollout_set_smem(h->smem_bytes);
+  // K_rollout: one-warp CTAs.  Horizons with a lane per stage (N+1 <= 32) run the short form of the ADMM phases.
+  h->short_form = p.N + 1 <= 32;
+  if (const char* fe = getenv("CUDAMPC_FORM")) { if (!strcmp(fe, "general")) h->short_form = false; }     // tuning knob
+  e = rollout_set_smem(h->short_form, h->smem_bytes);
   int occ = 0;
-  if (e == cudaSuccess) e = rollout_occupancy(h->smem_bytes, &occ);
+  if (e == cudaSuccess) e = rollout_occupancy(h->short_form, h->smem_bytes, &occ);
   if (e != cudaSuccess || occ < 1) { delete h; return fail(nullptr, CUDAMPC_ERR_CUDA, "CUDA failure: %s", cudaGetErrorString(e)); }
   h->roll_per_sm = occ;
   // K_solve: one CTA per SM with P independent groups.  P <= 8: with more resident warps the 255-register budget of the
@@ -353,7 +367,7 @@ int cudampc_create(const cudampc_params* params, int max_batch, int device, cuda
     h->grp_P = P;
     h->grp_wpp = (P <= 2 && p.N + 1 > 32) ? 2 : 1;
     if (const char* we = getenv("CUDAMPC_WPP")) { int v = atoi(we); if (v == 1 || (v == 2 && P <= 2)) h->grp_wpp = v; }
-    h->variant = h->grp_wpp == 2 ? SOLVE_W2 : SOLVE_W1;
+    h->variant = h->grp_wpp == 2 ? SOLVE_W2 : (h->short_form ? SOLVE_W1_SHORT : SOLVE_W1);
     h->grp_smem = P * (F * (int)sizeof(double) + (int)sizeof(GroupShared)) + 16;
     e = solve_set_smem(h->variant, h->grp_smem);
     if (e != cudaSuccess) { delete h; return fail(nullptr, CUDAMPC_ERR_CUDA, "CUDA failure: %s", cudaGetErrorString(e)); }
@@ -370,10 +384,6 @@ int cudampc_create(const cudampc_params* params, int max_batch, int device, cuda
   if (e == cudaSuccess) e = cudaMalloc(&h->tags, sizeof(unsigned long long) * 32);
   if (e == cudaSuccess) e = cudaMemset(h->tags, 0, sizeof(unsigned long long) * 32);
 #endif
-  if (e == cudaSuccess) e = cudaMalloc(&h->d_in, h->in_doubles * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc(&h->d_out, h->out_doubles * sizeof(double));
-  if (e == cudaSuccess) e = cudaMallocHost(&h->h_in, h->in_doubles * sizeof(double));
-  if (e == cudaSuccess) e = cudaMallocHost(&h->h_out, h->out_doubles * sizeof(double));
   if (e == cudaSuccess) e = cudaMemset(h->warm, 0, ws);
   if (e != cudaSuccess) {
     snprintf(g_create_err, sizeof g_create_err, "CUDA failure: allocation -> %s", cudaGetErrorString(e));
@@ -506,6 +516,10 @@ int cudampc_solve_batch_host(cudampc_handle* h, int batch, const double* x0, con
   cudaStream_t st = (cudaStream_t)stream;
   const int N = h->N;
   const size_t B = (size_t)batch;
+  if (!h->d_in) {          // device staging of the host path: allocated on first use (a device-only caller never pays for it)
+    CU(h, cudaMalloc(&h->d_in, h->in_doubles * sizeof(double)));
+    CU(h, cudaMalloc(&h->d_out, h->out_doubles * sizeof(double)));
+  }
   const size_t n_x0 = 4 * B, n_ref = 4 * (size_t)(N + 1) * B, n_up = 2 * B;
   const size_t n_u0 = 2 * B, n_xp = 4 * (size_t)(N + 1) * B, n_upo = 2 * (size_t)N * B;
   double* d_x0 = h->d_in; double* d_ref = d_x0 + n_x0; double* d_up = d_ref + n_ref;
@@ -521,6 +535,7 @@ int cudampc_solve_batch_host(cudampc_handle* h, int batch, const double* x0, con
     if (u_prev) CU(h, cudaMemcpyAsync(d_up, u_prev, n_up * sizeof(double), cudaMemcpyHostToDevice, st));
     else CU(h, cudaMemsetAsync(d_up, 0, n_up * sizeof(double), st));
   } else {
+    if (!h->h_in) CU(h, cudaMallocHost(&h->h_in, h->in_doubles * sizeof(double)));       // pinned staging for pageable callers
     memcpy(h->h_in, x0, n_x0 * sizeof(double));
     memcpy(h->h_in + n_x0, ref, n_ref * sizeof(double));
     if (u_prev) memcpy(h->h_in + n_x0 + n_ref, u_prev, n_up * sizeof(double));
@@ -544,6 +559,7 @@ int cudampc_solve_batch_host(cudampc_handle* h, int batch, const double* x0, con
     CU(h, cudaStreamSynchronize(st));
     return CUDAMPC_OK;
   }
+  if (!h->h_out) CU(h, cudaMallocHost(&h->h_out, h->out_doubles * sizeof(double)));
   const size_t n_out = n_u0 + n_xp + n_upo + 2 * B + 3 * B;   // 6 int32 per problem = 3 doubles
   CU(h, cudaMemcpyAsync(h->h_out, h->d_out, n_out * sizeof(double), cudaMemcpyDeviceToHost, st));
   CU(h, cudaStreamSynchronize(st));
@@ -601,7 +617,7 @@ int cudampc_rollout_batch(cudampc_handle* h, int batch, const double* ref_global
   {
     int grid = h->sms * h->roll_per_sm;
     if (grid > batch) grid = batch;
-    rollout_launch(grid, h->smem_bytes, st, h->p, s, c, a);
+    rollout_launch(h->short_form, grid, h->smem_bytes, st, h->p, s, c, a);
   }
   h->launches++;
   CU(h, cudaGetLastError());

@@ -1116,6 +1116,69 @@ MPC_HD void admm_update_stage_oe(const View& w, const Params& p, const IterConst
   admm_update_vals(w, p, c, k, xt, xn, inputs_before ? xp[4] : 0.0, inputs_before ? xp[5] : 0.0);
 }
 
+// Short horizons (N+1 <= 32: every stage has its own lane of one warp).  The heavy parts of the two phases do not depend
+// on the other parity - A2 reads the neighbours' STATE, A1 reads x-tilde of all stages once it exists - so they run as ONE
+// pass over all stages; only the two light block-solve steps remain parity passes:
+//   rhs   : all k: b_k (odd k: stored as t_k = D_k^-1 b_k)   ->   even k: b'_k = b_k - E_k t_{k-1} - E_{k+1}' t_{k+1}
+//   update: odd k: x~_k = t_k - D_k^-1 (E_k x~_{k-1} + E_{k+1}' x~_{k+1})   ->   all k: A1
+MPC_HD void admm_rhs_stage_short(const View& w, const Params& p, const IterConst& c, const OEView& oe, int k) {
+  double val[6];
+  admm_rhs_vals(w, p, c, k, val);
+  if (k & 1) {
+    double di[OE_SYM], t[6];
+    sym_load(oe.dinv + OE_SYM * (k >> 1), di);
+    symv6(di, val, t);
+    row_store(w.nx(k), t);
+  } else {
+    row_store(w.nx(k), val);
+  }
+}
+MPC_HD void oe_even_fixup(const View& w, const Params& p, const IterConst& c, int k) {
+  const int N = w.N;
+  double val[6], t[6], y[6];
+  row_load(w.nx(k), val);
+  if (k >= 1) {
+    row_load(w.nx(k - 1), t);
+    cross_mul(w.rec(k - 1) + R_LIN, p.dt, c.rho_eq, c.kap, k < N, t, y);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) val[j] -= y[j];
+  }
+  if (k + 1 <= N) {
+    row_load(w.nx(k + 1), t);
+    cross_mul_t(w.rec(k) + R_LIN, p.dt, c.rho_eq, c.kap, k + 1 < N, t, y);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) val[j] -= y[j];
+  }
+  row_store(w.nx(k), val);
+}
+MPC_HD void oe_expand_odd(const View& w, const Params& p, const IterConst& c, const OEView& oe, int k) {
+  const int N = w.N;
+  double xp[6], xn[6], di[OE_SYM], t[6], v[6], y[6], u[6];
+  row_load(w.nx(k - 1), xp);
+  row_load(w.nx(k), t);
+  cross_mul(w.rec(k - 1) + R_LIN, p.dt, c.rho_eq, c.kap, k < N, xp, v);
+  if (k + 1 <= N) {
+    row_load(w.nx(k + 1), xn);
+    cross_mul_t(w.rec(k) + R_LIN, p.dt, c.rho_eq, c.kap, k + 1 < N, xn, y);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) v[j] += y[j];
+  }
+  sym_load(oe.dinv + OE_SYM * (k >> 1), di);
+  symv6(di, v, u);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) t[j] -= u[j];
+  row_store(w.nx(k), t);
+}
+MPC_HD void admm_update_stage_short(const View& w, const Params& p, const IterConst& c, int k) {
+  const int N = w.N;
+  double xt[6], xn[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, xp[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  row_load(w.nx(k), xt);
+  if (k >= 1) row_load(w.nx(k - 1), xp);
+  if (k + 1 <= N) row_load(w.nx(k + 1), xn);
+  const bool inputs_before = k > 0 && k < N;
+  admm_update_vals(w, p, c, k, xt, xn, inputs_before ? xp[4] : 0.0, inputs_before ? xp[5] : 0.0);
+}
+
 // ----------------------------------------------------------------------------------------------
 // Residuals of the current iterate (x, z = clip(v), y): per-stage partial maxima
 //   r[0] |Ax - z|, r[1] |Ax|, r[2] |z|, r[3] |Px + q + A'y|, r[4] |Px|, r[5] |A'y|, r[6] |q|

@@ -21,7 +21,7 @@ struct BatchArgs {
 // K_solve: batched MPCController.solve.  The CTA holds P problems, each owned by a group of WPP warps (GroupExec).
 // <256,1>: P <= 8 one-warp groups, 255 registers; <128,2>: P <= 2 two-warp groups for long horizons.
 // ------------------------------------------------------------------------------------------------
-template <int MAXT, int WPP>
+template <int MAXT, int WPP, bool SHORT>
 __global__ void __launch_bounds__(MAXT, 1) mpc_solve_kernel(Params p, Settings s, BatchArgs a, int P, int F) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(MAXT, 1) mpc_solve_kernel(Params p, Settings s
     io.status = a.status + b; io.iters = a.iters + b;
     io.pri_res = a.pri ? a.pri + b : nullptr; io.dua_res = a.dua ? a.dua + b : nullptr;
     io.info = a.info ? a.info + 4 * (size_t)b : nullptr;
-    solve_problem(ex, w, p, s, io);
+    solve_problem<SHORT>(ex, w, p, s, io);
     ex.group_sync();
   }
 }
@@ -77,7 +77,7 @@ __device__ __forceinline__ void f_discrete_dev(const Params& p, const double* x,
 }
 
 // One vehicle, all steps (TrajectoryTracker.track loop body, control_stage.py:100-150), generic in the execution policy
-template <class Exec>
+template <bool SHORT, class Exec>
 __device__ __forceinline__ void rollout_vehicle(Exec& ex, const View& w, const Params& p, const Settings& s,
                                                 const cudampc_rollout_cfg& cfg, const RolloutArgs& a, int b) {
   const int N = p.N;
@@ -102,6 +102,8 @@ __device__ __forceinline__ void rollout_vehicle(Exec& ex, const View& w, const P
   });
   int path_idx = 0, flags = 0, nst = 0;
   for (int step = 0; step < cfg.sim_steps; ++step) {
+    unsigned long long t_step = 0;
+    if (cfg.step_ns_dev) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_step));
     int* st_out = a.step_status ? a.step_status + (size_t)cfg.sim_steps * b + step : reinterpret_cast<int*>(wkb + 10);
     int* it_out = a.step_iters ? a.step_iters + (size_t)cfg.sim_steps * b + step : reinterpret_cast<int*>(wkb + 10) + 1;
     ProblemIO io;
@@ -112,7 +114,7 @@ __device__ __forceinline__ void rollout_vehicle(Exec& ex, const View& w, const P
     io.status = st_out; io.iters = it_out; io.pri_res = nullptr; io.dua_res = nullptr; io.info = nullptr;
     Settings ss = s;
     ss.warm_start = (s.warm_start && step > 0) ? 1 : 0;
-    solve_problem(ex, w, p, ss, io);
+    solve_problem<SHORT>(ex, w, p, ss, io);
     ex.group_sync();
     int status = *st_out;
     if (status != STATUS_SOLVED && status != STATUS_SOLVED_INACCURATE && cfg.relax_on_failure) {
@@ -122,7 +124,7 @@ __device__ __forceinline__ void rollout_vehicle(Exec& ex, const View& w, const P
       pr.du_lo[1] -= cfg.relax_ddelta; pr.du_hi[1] += cfg.relax_ddelta;
       io.ref.vscale = cfg.relax_v_scale;
       ss.warm_start = 0;
-      solve_problem(ex, w, pr, ss, io);
+      solve_problem<SHORT>(ex, w, pr, ss, io);
       ex.group_sync();
       status = *st_out;
       flags |= 4;
@@ -143,6 +145,11 @@ __device__ __forceinline__ void rollout_vehicle(Exec& ex, const View& w, const P
       double dx = xn[0] - refg[4 * (size_t)path_idx], dy = xn[1] - refg[4 * (size_t)path_idx + 1];
       if (dx * dx + dy * dy > cfg.advance_dist2) path_idx += 1;
     }
+    if (cfg.step_ns_dev) {
+      unsigned long long t_end;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+      ex.single([&]() { cfg.step_ns_dev[(size_t)cfg.sim_steps * b + step] = (int)(t_end - t_step); });
+    }
     if (hypot(xn[0] - a.goal[2 * (size_t)b], xn[1] - a.goal[2 * (size_t)b + 1]) < cfg.goal_radius) { flags |= 1; break; }
   }
   // rows after the vehicle stopped
@@ -154,23 +161,25 @@ __device__ __forceinline__ void rollout_vehicle(Exec& ex, const View& w, const P
   ex.single([&]() { a.n_steps[b] = nst; a.flags[b] = flags; });
 }
 
-template <int ONE_WARP>      // (a template only so that the kernel is emitted by the one translation unit that launches it)
+template <bool SHORT>
 __global__ void __launch_bounds__(32) mpc_rollout_kernel(Params p, Settings s, cudampc_rollout_cfg cfg, RolloutArgs a) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;
   int fpad, xpad; layout_pads(p.N, fpad, xpad);
   View w{smem, p.N, fpad, xpad};
   GroupExec<1> ex{lane, 0, nullptr};
-  for (int b = ex.fetch(a.counter); b < a.batch; b = ex.fetch(a.counter)) rollout_vehicle(ex, w, p, s, cfg, a, b);
+  for (int b = ex.fetch(a.counter); b < a.batch; b = ex.fetch(a.counter)) rollout_vehicle<SHORT>(ex, w, p, s, cfg, a, b);
 }
 
 
 // ------------------------------------------------------------------------------------------------
 // Instantiations and their launchers
 // ------------------------------------------------------------------------------------------------
-enum SolveVariant { SOLVE_W1 = 0, SOLVE_W2 = 1 };
+// K_solve: one warp per problem with the short form of the phases (N+1 <= 32) or the general form, two warps per problem
+// (general form, long horizons); K_rollout: one warp per vehicle, short or general form.
+enum SolveVariant { SOLVE_W1_SHORT = 0, SOLVE_W1 = 1, SOLVE_W2 = 2 };
 cudaError_t solve_set_smem(int variant, int bytes);
 void solve_launch(int variant, int grid, int threads, int smem, cudaStream_t st, const Params& p, const Settings& s, const BatchArgs& a, int P, int F);
-cudaError_t rollout_set_smem(int bytes);
-cudaError_t rollout_occupancy(int bytes, int* blocks_per_sm);
-void rollout_launch(int grid, int smem, cudaStream_t st, const Params& p, const Settings& s, const cudampc_rollout_cfg& cfg, const RolloutArgs& a);
+cudaError_t rollout_set_smem(bool short_form, int bytes);
+cudaError_t rollout_occupancy(bool short_form, int bytes, int* blocks_per_sm);
+void rollout_launch(bool short_form, int grid, int smem, cudaStream_t st, const Params& p, const Settings& s, const cudampc_rollout_cfg& cfg, const RolloutArgs& a);

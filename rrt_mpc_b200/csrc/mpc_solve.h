@@ -41,7 +41,9 @@ MPC_HD Residuals compute_residuals(Exec& ex, const View& w, const Params& p, con
   return o;
 }
 
-template <class Exec>
+// SHORT: form of the ADMM phases for horizons with N+1 <= 32 (one lane per stage; mpc_core.h admm_rhs_stage_short);
+// the general form runs the phases one parity of stages at a time.  Separate instantiations, so a kernel carries one form.
+template <bool SHORT, class Exec>
 MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settings& s, const ProblemIO& io) {
   const int N = w.N;
   const int NS = N + 1;
@@ -225,8 +227,13 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
       need_factor = false;
     }
     ex.tag(6);
+    if constexpr (SHORT) {
+      ex.stages(NS, [&](int k) { admm_rhs_stage_short(w, p, ic, oe, k); });
+      ex.stages_par(NS, 0, [&](int k) { oe_even_fixup(w, p, ic, k); });
+    } else {
 #pragma unroll 1
-    for (int par = 1; par >= 0; --par) ex.stages_par(NS, par, [&](int k) { admm_rhs_stage_oe(w, p, ic, oe, k); });
+      for (int par = 1; par >= 0; --par) ex.stages_par(NS, par, [&](int k) { admm_rhs_stage_oe(w, p, ic, oe, k); });
+    }
     ++it;
     ex.tag(16);
     ex.oe_forward(w, oe);
@@ -235,8 +242,13 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
     ex.tag(18);
     ex.oe_backward(w, oe); ++n_solve;
     ex.tag(2);
+    if constexpr (SHORT) {
+      ex.stages_par(NS, 1, [&](int k) { oe_expand_odd(w, p, ic, oe, k); });
+      ex.stages(NS, [&](int k) { admm_update_stage_short(w, p, ic, k); });
+    } else {
 #pragma unroll 1
-    for (int par = 1; par >= 0; --par) ex.stages_par(NS, par, [&](int k) { admm_update_stage_oe(w, p, ic, oe, k); });
+      for (int par = 1; par >= 0; --par) ex.stages_par(NS, par, [&](int k) { admm_update_stage_oe(w, p, ic, oe, k); });
+    }
     after_update();
   }
   ex.tag(7);

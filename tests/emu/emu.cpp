@@ -76,6 +76,9 @@ static void unpack(const double* par, const double* set, int N, Params& p, Setti
   s.warm_start = (int)set[i++]; s.polish_retry = (int)set[i++]; s.early_polish = (int)set[i++]; s.early_polish_start = (int)set[i++];
 }
 
+static int g_form = -1;      // -1: what the library picks (short form for N+1 <= 32), 0: general form, 1: short form
+void emu_set_form(int f) { g_form = f; }
+
 int emu_solve_batch(const double* par, const double* set, int N, int B, int reverse,
                     const double* x0, const double* ref, const double* u_prev, double* warm,
                     double* u0, double* Xp, double* Up, int* status, int* iters, double* pri, double* dua, int* info) {
@@ -93,7 +96,7 @@ int emu_solve_batch(const double* par, const double* set, int N, int B, int reve
     Settings sb = s;
     if (!warm) sb.warm_start = 0;
     EmuExec ex{reverse};
-    solve_problem(ex, w, p, sb, io);
+    if (g_form == 1 || (g_form < 0 && N + 1 <= 32)) solve_problem<true>(ex, w, p, sb, io); else solve_problem<false>(ex, w, p, sb, io);
   }
   return 0;
 }

@@ -49,6 +49,11 @@ def solve(p, x0, ref, up, reverse=0, warm=None, **s):
     return out
 
 
+def set_form(form):
+    """-1: what the library picks (short form of the phases for N+1 <= 32), 0: general (parity) form, 1: short form."""
+    lib().emu_set_form(int(form))
+
+
 def warm_size(N):
     return lib().emu_warm_size(N)
 

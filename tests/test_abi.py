@@ -31,7 +31,7 @@ def test_struct_layouts_and_defaults():
     lib = _lib.load()
     assert C.sizeof(_lib.Params) == 8 * 2 + 8 + 8 * (16 + 4 + 16 + 4 + 2 + 4 + 3)
     assert C.sizeof(_lib.Settings) == 8 * 10 + 4 * 10
-    assert C.sizeof(_lib.RolloutCfg) == 8 + 8 * 5
+    assert C.sizeof(_lib.RolloutCfg) == 8 + 8 * 5 + 8
     s = _lib.Settings()
     lib.cudampc_default_settings(C.byref(s))
     # the reference's OSQP call, src/control/mpc_controller.py:121-131

@@ -21,9 +21,9 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import bench
     from rrt_mpc_b200.synthetic import make_batch
-    per = 300
-    start, count = bench.shard_range(rank, world, per)
-    x0, ref, up = make_batch(per * world, 20, seed=5, start=start, count=count)
+    total = 601                                                          # a global batch that does not divide evenly
+    start, count = bench.shard_range(rank, world, total)
+    x0, ref, up = make_batch(total, 20, seed=5, start=start, count=count)
     local = {"ms_total": 10.0 + rank, "solves": float(count), "checksum": float(x0.sum() + ref.sum() + up.sum())}
     allm = bench.gather_metrics(local, world)
     q.put((rank, start, count, allm))
@@ -43,15 +43,17 @@ def test_two_rank_shards_and_gather():
         p.join(timeout=60)
         assert p.exitcode == 0
     from rrt_mpc_b200.synthetic import make_batch
-    full = make_batch(600, 20, seed=5)
+    full = make_batch(601, 20, seed=5)
     (r0, s0, c0, m0), (r1, s1, c1, m1) = got
-    assert (s0, c0, s1, c1) == (0, 300, 300, 300)                       # disjoint, covering shards
+    assert (s0, c0, s1, c1) == (0, 301, 301, 300)                       # disjoint, covering shards of the fixed global batch (strong scaling)
     assert m0 == m1 and len(m0) == 2                                    # every rank sees every rank's metrics
-    chk = [float(full[0][a:b].sum() + full[1][a:b].sum() + full[2][a:b].sum()) for a, b in ((0, 300), (300, 600))]
+    chk = [float(full[0][a:b].sum() + full[1][a:b].sum() + full[2][a:b].sum()) for a, b in ((0, 301), (301, 601))]
     assert np.allclose([m0[0]["checksum"], m0[1]["checksum"]], chk, rtol=1e-12)
     # whole-job value = all solves / max-over-ranks time
     t = max(m["ms_total"] for m in m0)
-    assert t == 11.0 and sum(m["solves"] for m in m0) == 600.0
+    assert t == 11.0 and sum(m["solves"] for m in m0) == 601.0
+    import bench
+    assert [bench.shard_range(r, 8, 1 << 20) for r in (0, 7)] == [(0, 131072), (917504, 131072)]       # configs[4] over 8 GPUs
 
 
 def test_flop_model_matches_baseline_table():

@@ -172,3 +172,24 @@ def test_warm_start_from_a_never_solved_slot_starts_cold():
     hot = E.solve(p, g["n20_x0"][:nb], g["n20_ref"][:nb], g["n20_up"][:nb], warm=warm, warm_start=1, polish_passes=3, **TIGHT)
     cold = E.solve(p, g["n20_x0"][:nb], g["n20_ref"][:nb], g["n20_up"][:nb], polish_passes=3, **TIGHT)
     assert np.array_equal(hot["iters"], cold["iters"])
+
+
+def test_short_and_general_form_of_the_phases_agree():
+    """Horizons with N+1 <= 32 run the ADMM phases as one pass over all stages plus two light parity steps
+    (solve_problem<true>), longer ones one parity of stages at a time (solve_problem<false>): the same arithmetic per stage,
+    so iterates agree to the last bit."""
+    g = load_golden("optima.npz")
+    p = oracle_params(20)
+    nb = 6
+    kw = dict(polish_passes=5, polish_retry=2, early_polish=1, **TIGHT)
+    try:
+        E.set_form(1)
+        a = E.solve(p, g["n20_x0"][:nb], g["n20_ref"][:nb], g["n20_up"][:nb], **kw)
+        ar = E.solve(p, g["n20_x0"][:nb], g["n20_ref"][:nb], g["n20_up"][:nb], reverse=1, **kw)
+        E.set_form(0)
+        b = E.solve(p, g["n20_x0"][:nb], g["n20_ref"][:nb], g["n20_up"][:nb], **kw)
+    finally:
+        E.set_form(-1)
+    for k in ("u0", "Xp", "Up", "iters", "status"):
+        assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], ar[k])
+    assert np.abs(a["u0"] - g["n20_u0"][:nb]).max() < 1e-8
