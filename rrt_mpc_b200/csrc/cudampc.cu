@@ -172,7 +172,7 @@ struct cudampc_handle {
   int sms, smem_bytes, roll_per_sm;   // K_rollout: one-warp CTAs of smem_bytes each, roll_per_sm resident per SM
   int grp_P, grp_wpp, grp_smem;        // K_solve: one CTA per SM with grp_P groups of grp_wpp warps
   int variant;                         // SolveVariant
-  bool short_form;                     // N+1 <= 32: short form of the ADMM phases (K_solve one-warp groups, K_rollout)
+  int form;                            // form of the ADMM phases (mpc_solve.h FORM_*): K_solve one-warp groups, K_rollout
   unsigned long long* tags;            // dev builds (MPC_TIMING): per-tag cycle counters
   long long launches;
   char err[512];
@@ -181,23 +181,33 @@ struct cudampc_handle {
 static char g_create_err[512] = "";
 
 // launchers of the kernel instantiations (mpc_kernels_tu.cu, one translation unit each)
-cudaError_t solve_set_smem_0(int), solve_set_smem_1(int), solve_set_smem_2(int);
+cudaError_t solve_set_smem_0(int), solve_set_smem_1(int), solve_set_smem_2(int), solve_set_smem_3(int), solve_set_smem_4(int);
 void solve_launch_0(int, int, int, cudaStream_t, const Params&, const Settings&, const BatchArgs&, int, int);
 void solve_launch_1(int, int, int, cudaStream_t, const Params&, const Settings&, const BatchArgs&, int, int);
 void solve_launch_2(int, int, int, cudaStream_t, const Params&, const Settings&, const BatchArgs&, int, int);
-cudaError_t rollout_set_smem_short(int), rollout_set_smem_general(int), rollout_occupancy_short(int, int*), rollout_occupancy_general(int, int*);
+void solve_launch_3(int, int, int, cudaStream_t, const Params&, const Settings&, const BatchArgs&, int, int);
+void solve_launch_4(int, int, int, cudaStream_t, const Params&, const Settings&, const BatchArgs&, int, int);
+cudaError_t rollout_set_smem_short(int), rollout_set_smem_general(int), rollout_set_smem_pair(int);
+cudaError_t rollout_occupancy_short(int, int*), rollout_occupancy_general(int, int*), rollout_occupancy_pair(int, int*);
 void rollout_launch_short(int, int, cudaStream_t, const Params&, const Settings&, const cudampc_rollout_cfg&, const RolloutArgs&);
 void rollout_launch_general(int, int, cudaStream_t, const Params&, const Settings&, const cudampc_rollout_cfg&, const RolloutArgs&);
-cudaError_t solve_set_smem(int v, int bytes) { return v == 0 ? solve_set_smem_0(bytes) : v == 1 ? solve_set_smem_1(bytes) : solve_set_smem_2(bytes); }
+void rollout_launch_pair(int, int, cudaStream_t, const Params&, const Settings&, const cudampc_rollout_cfg&, const RolloutArgs&);
+cudaError_t solve_set_smem(int v, int bytes) { return v == 0 ? solve_set_smem_0(bytes) : v == 1 ? solve_set_smem_1(bytes) : v == 2 ? solve_set_smem_2(bytes) : v == 3 ? solve_set_smem_3(bytes) : solve_set_smem_4(bytes); }
 void solve_launch(int v, int grid, int threads, int smem, cudaStream_t st, const Params& p, const Settings& s, const BatchArgs& a, int P, int F) {
   if (v == 0) solve_launch_0(grid, threads, smem, st, p, s, a, P, F);
   else if (v == 1) solve_launch_1(grid, threads, smem, st, p, s, a, P, F);
-  else solve_launch_2(grid, threads, smem, st, p, s, a, P, F);
+  else if (v == 2) solve_launch_2(grid, threads, smem, st, p, s, a, P, F);
+  else if (v == 3) solve_launch_3(grid, threads, smem, st, p, s, a, P, F);
+  else solve_launch_4(grid, threads, smem, st, p, s, a, P, F);
 }
-cudaError_t rollout_set_smem(bool sf, int bytes) { return sf ? rollout_set_smem_short(bytes) : rollout_set_smem_general(bytes); }
-cudaError_t rollout_occupancy(bool sf, int bytes, int* n) { return sf ? rollout_occupancy_short(bytes, n) : rollout_occupancy_general(bytes, n); }
-void rollout_launch(bool sf, int grid, int smem, cudaStream_t st, const Params& p, const Settings& s, const cudampc_rollout_cfg& cfg, const RolloutArgs& a) {
-  if (sf) rollout_launch_short(grid, smem, st, p, s, cfg, a); else rollout_launch_general(grid, smem, st, p, s, cfg, a);
+cudaError_t rollout_set_smem(int f, int bytes) { return f == FORM_SHORT ? rollout_set_smem_short(bytes) : f == FORM_PAIR ? rollout_set_smem_pair(bytes) : rollout_set_smem_general(bytes); }
+cudaError_t rollout_occupancy(int f, int bytes, int* n) {
+  return f == FORM_SHORT ? rollout_occupancy_short(bytes, n) : f == FORM_PAIR ? rollout_occupancy_pair(bytes, n) : rollout_occupancy_general(bytes, n);
+}
+void rollout_launch(int f, int grid, int smem, cudaStream_t st, const Params& p, const Settings& s, const cudampc_rollout_cfg& cfg, const RolloutArgs& a) {
+  if (f == FORM_SHORT) rollout_launch_short(grid, smem, st, p, s, cfg, a);
+  else if (f == FORM_PAIR) rollout_launch_pair(grid, smem, st, p, s, cfg, a);
+  else rollout_launch_general(grid, smem, st, p, s, cfg, a);
 }
 
 // Every entry point runs on the handle's device and leaves the caller's current device as it found it.
@@ -348,12 +358,17 @@ int cudampc_create(const cudampc_params* params, int max_batch, int device, cuda
   h->smem_bytes = F * (int)sizeof(double);
   const int optin = (int)prop.sharedMemPerBlockOptin;
   if (h->smem_bytes + (int)sizeof(GroupShared) > optin) { delete h; return fail(nullptr, CUDAMPC_ERR_UNSUPPORTED, "%s", "horizon too long for one problem per 227 KB of shared memory"); }
-  // K_rollout: one-warp CTAs.  Horizons with a lane per stage (N+1 <= 32) run the short form of the ADMM phases.
-  h->short_form = p.N + 1 <= 32;
-  if (const char* fe = getenv("CUDAMPC_FORM")) { if (!strcmp(fe, "general")) h->short_form = false; }     // tuning knob
-  e = rollout_set_smem(h->short_form, h->smem_bytes);
+  // K_rollout: one-warp CTAs.  Form of the ADMM phases (mpc_solve.h): a lane per stage for N+1 <= 32 (short), a lane per
+  // pair of stages for N+1 <= 64 (pair), one parity of stages at a time beyond (general).
+  h->form = p.N + 1 <= 32 ? FORM_SHORT : FORM_GENERAL;      // the pair form (N+1 <= 64) is opt-in: measured slower (profiles/README.md)
+  if (const char* fe = getenv("CUDAMPC_FORM")) {                                                          // tuning knob
+    if (!strcmp(fe, "general")) h->form = FORM_GENERAL;
+    else if (!strcmp(fe, "pair") && p.N + 1 <= 64) h->form = FORM_PAIR;
+    else if (!strcmp(fe, "short") && p.N + 1 <= 32) h->form = FORM_SHORT;
+  }
+  e = rollout_set_smem(h->form, h->smem_bytes);
   int occ = 0;
-  if (e == cudaSuccess) e = rollout_occupancy(h->short_form, h->smem_bytes, &occ);
+  if (e == cudaSuccess) e = rollout_occupancy(h->form, h->smem_bytes, &occ);
   if (e != cudaSuccess || occ < 1) { delete h; return fail(nullptr, CUDAMPC_ERR_CUDA, "CUDA failure: %s", cudaGetErrorString(e)); }
   h->roll_per_sm = occ;
   // K_solve: one CTA per SM with P independent groups.  P <= 8: with more resident warps the 255-register budget of the
@@ -361,13 +376,17 @@ int cudampc_create(const cudampc_params* params, int max_batch, int device, cuda
   // latency-bound there); at P >= 3 the extra barriers cost more than the second warp saves (measured again in round 2:
   // branch item-form-experiment).
   {
+    int solve_form = h->form;                                         // K_solve may run the register form (K_rollout: one warp)
+    if (const char* fe = getenv("CUDAMPC_FORM")) { if (!strcmp(fe, "reg") && p.N + 1 <= 64) solve_form = FORM_REG; }
     int P = (optin - 64) / (F * (int)sizeof(double) + (int)sizeof(GroupShared));
     if (P > 8) P = 8;
     if (const char* pe = getenv("CUDAMPC_P")) { int v = atoi(pe); if (v >= 1 && v < P) P = v; }   // tuning knobs
     h->grp_P = P;
     h->grp_wpp = (P <= 2 && p.N + 1 > 32) ? 2 : 1;
     if (const char* we = getenv("CUDAMPC_WPP")) { int v = atoi(we); if (v == 1 || (v == 2 && P <= 2)) h->grp_wpp = v; }
-    h->variant = h->grp_wpp == 2 ? SOLVE_W2 : (h->short_form ? SOLVE_W1_SHORT : SOLVE_W1);
+    h->variant = h->grp_wpp == 2 ? SOLVE_W2 : (h->form == FORM_SHORT ? SOLVE_W1_SHORT : h->form == FORM_PAIR ? SOLVE_W1_PAIR : SOLVE_W1);
+    // register form (mpc_reg.h): two warps per problem, at most 4 problems (8 warps x 255 registers; more warps would cap the registers at 168)
+    if (solve_form == FORM_REG) { if (P > 4) { P = 4; h->grp_P = 4; } h->grp_wpp = 2; h->variant = SOLVE_W2_REG; }
     h->grp_smem = P * (F * (int)sizeof(double) + (int)sizeof(GroupShared)) + 16;
     e = solve_set_smem(h->variant, h->grp_smem);
     if (e != cudaSuccess) { delete h; return fail(nullptr, CUDAMPC_ERR_CUDA, "CUDA failure: %s", cudaGetErrorString(e)); }
@@ -617,7 +636,7 @@ int cudampc_rollout_batch(cudampc_handle* h, int batch, const double* ref_global
   {
     int grid = h->sms * h->roll_per_sm;
     if (grid > batch) grid = batch;
-    rollout_launch(h->short_form, grid, h->smem_bytes, st, h->p, s, c, a);
+    rollout_launch(h->form, grid, h->smem_bytes, st, h->p, s, c, a);
   }
   h->launches++;
   CU(h, cudaGetLastError());

@@ -1179,6 +1179,11 @@ MPC_HD void admm_update_stage_short(const View& w, const Params& p, const IterCo
   admm_update_vals(w, p, c, k, xt, xn, inputs_before ? xp[4] : 0.0, inputs_before ? xp[5] : 0.0);
 }
 
+}  // namespace mpc
+#include "mpc_pair.h"
+#include "mpc_reg.h"
+namespace mpc {
+
 // ----------------------------------------------------------------------------------------------
 // Residuals of the current iterate (x, z = clip(v), y): per-stage partial maxima
 //   r[0] |Ax - z|, r[1] |Ax|, r[2] |z|, r[3] |Px + q + A'y|, r[4] |Px|, r[5] |A'y|, r[6] |q|

@@ -65,73 +65,86 @@ __device__ __forceinline__ double lds_f64(unsigned a) { double v; asm volatile("
 __device__ __forceinline__ void sts_f64_if(bool p, unsigned a, double v) {
   asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.shared.f64 [%1], %2; }" ::"r"((unsigned)p), "r"(a), "d"(v) : "memory");
 }
+// The twelve row lanes run the sweep inside ONE divergent region (the other twenty lanes of the warp wait at its end), with
+// warp barriers and shuffles over the twelve-lane mask.  With all 32 lanes executing the loads (the idle ones on duplicate
+// addresses, to keep the warp converged) every 128-bit load cost the shared-memory pipe 4-5 wavefronts instead of 2: with
+// five chain warps per SM that saturated the pipe - 108 cycles per step alone, 170 with five warps sweeping
+// (tools/microbench/oe_bench.cu).  The loop is branch-free between the two halves: both run the trip count of the longer
+// one, a half that is done keeps computing on in-bounds words of the workspace and stores nothing (predicated).
+#define MPC_ROW_LANES 0x00000fffu
 __device__ __forceinline__ void oe_forward_lanes(int lane, const View& w, const OEView& oe) {
-  const bool act = lane < 12;
-  const bool bottom = (lane / 6) & 1;
-  const int r = lane % 6;
-  const OEHalf h = oe_half(w, oe, bottom);
-  const int cnt = h.cnt, cmax = oe.jm > oe.nb ? oe.jm : oe.nb;     // uniform trip count
-  const int xs = h.xstep * 8;                                      // bytes between consecutive local rows (+-48)
-  const unsigned xlast = smem_u32(h.xlast) + 8 * r;
-  unsigned xrow = smem_u32(h.x0) + xs;                             // row of local stage i (i = 1)
-  unsigned gp = smem_u32(h.g0) + 48 * r;                           // row r of the block of step i
-  double a[6], gA[6], gB[6], nbA, nbB, y;
-  lds_row(smem_u32(h.x0), a);                                      // y_0 = b'_0
-  double ymid = lds_f64(xlast);                                    // the half's term for the middle if it has no step
-  lds_row(gp, gA); nbA = lds_f64(cnt == 1 ? xlast : xrow + 8 * r);
-  for (int i = 1; i <= cmax; i += 2) {
-    lds_row(gp + 288, gB); nbB = lds_f64(i + 1 == cnt ? xlast : xrow + xs + 8 * r);          // step i+1
-    y = oe_row_dot(gA, nbA, a);
-    ymid = (i == cnt) ? y : ymid;
-    sts_f64_if(act && i < cnt, xrow + 8 * r, y);
-    __syncwarp();
-    lds_row(xrow, a);
-    if (i + 1 > cmax) break;
-    lds_row(gp + 576, gA); nbA = lds_f64(i + 2 == cnt ? xlast : xrow + 2 * xs + 8 * r);      // step i+2
-    y = oe_row_dot(gB, nbB, a);
-    ymid = (i + 1 == cnt) ? y : ymid;
-    sts_f64_if(act && i + 1 < cnt, xrow + xs + 8 * r, y);
-    __syncwarp();
-    lds_row(xrow + xs, a);
-    gp += 576; xrow += 2 * xs;
+  if (lane < 12) {
+    const bool bottom = lane >= 6;
+    const int r = bottom ? lane - 6 : lane;
+    const OEHalf h = oe_half(w, oe, bottom);
+    const int cnt = h.cnt, cmax = oe.jm > oe.nb ? oe.jm : oe.nb;     // uniform trip count
+    const int xs = h.xstep * 8;                                      // bytes between consecutive local rows (+-48)
+    const unsigned xlast = smem_u32(h.xlast) + 8 * r;
+    unsigned xrow = smem_u32(h.x0) + xs;                             // row of local stage i (i = 1)
+    unsigned gp = smem_u32(h.g0) + 48 * r;                           // row r of the block of step i
+    double a[6], gA[6], gB[6], nbA, nbB, y;
+    lds_row(smem_u32(h.x0), a);                                      // y_0 = b'_0
+    double ymid = lds_f64(xlast);                                    // the half's term for the middle if it has no step
+    lds_row(gp, gA); nbA = lds_f64(cnt == 1 ? xlast : xrow + 8 * r);
+    for (int i = 1; i <= cmax; i += 2) {
+      lds_row(gp + 288, gB); nbB = lds_f64(i + 1 == cnt ? xlast : xrow + xs + 8 * r);          // step i+1
+      y = oe_row_dot(gA, nbA, a);
+      ymid = (i == cnt) ? y : ymid;
+      sts_f64_if(i < cnt, xrow + 8 * r, y);
+      __syncwarp(MPC_ROW_LANES);
+      lds_row(xrow, a);
+      if (i + 1 > cmax) break;
+      lds_row(gp + 576, gA); nbA = lds_f64(i + 2 == cnt ? xlast : xrow + 2 * xs + 8 * r);      // step i+2
+      y = oe_row_dot(gB, nbB, a);
+      ymid = (i + 1 == cnt) ? y : ymid;
+      sts_f64_if(i + 1 < cnt, xrow + xs + 8 * r, y);
+      __syncwarp(MPC_ROW_LANES);
+      lds_row(xrow + xs, a);
+      gp += 576; xrow += 2 * xs;
+    }
+    // middle stage: x_m = S'_m^-1 (top term + bottom term); lanes r and r + 6 hold element r of the two terms
+    const double yo = __shfl_sync(MPC_ROW_LANES, ymid, bottom ? lane - 6 : lane + 6);
+    double* mrow = w.nx(2 * oe.jm);
+    if (lane < 6) mrow[r] = ymid + yo;
+    __syncwarp(MPC_ROW_LANES);
+    double xm = 0.0;
+    if (lane < 6) {
+      double s[6];
+      row_load(mrow, s);
+      xm = oe_sym_row(oe.sinv + OE_SYM * oe.jm, r, s);
+    }
+    __syncwarp(MPC_ROW_LANES);
+    if (lane < 6) mrow[r] = xm;
   }
-  // middle stage: x_m = S'_m^-1 (top term + bottom term); lanes r and r + 6 hold element r of the two terms
-  const double yo = __shfl_sync(0xffffffffu, ymid, bottom ? lane - 6 : (lane + 6) & 31);
-  double* mrow = w.nx(2 * oe.jm);
-  if (lane < 6) mrow[r] = ymid + yo;
-  __syncwarp();
-  double s[6];
-  row_load(mrow, s);
-  const double xm = oe_sym_row(oe.sinv + OE_SYM * oe.jm, r, s);
-  __syncwarp();
-  if (lane < 6) mrow[r] = xm;
   __syncwarp();
 }
 __device__ __forceinline__ void oe_backward_lanes(int lane, const View& w, const OEView& oe) {
-  const bool act = lane < 12;
-  const bool bottom = (lane / 6) & 1;
-  const int c = lane % 6;
-  const OEHalf h = oe_half(w, oe, bottom);
-  const int cmax = oe.jm > oe.nb ? oe.jm : oe.nb;
-  const int xs = h.xstep * 8;
-  int i = h.cnt - 1;                                               // local stage of this half at the current step (< 0: done)
-  unsigned xrow = smem_u32(h.x0) + xs * i;                         // row of local stage i
-  unsigned gp = smem_u32(h.g0) + 288 * i + 8 * c;                  // column c of the block of step i+1
-  double a[6], gA[6], gB[6], zA, zB;
-  lds_row(smem_u32(w.nx(2 * oe.jm)), a);                           // x_m
-  lds_col(gp, gA); zA = lds_f64(xrow + 8 * c);
-  for (int s = 0; s < cmax; s += 2, i -= 2) {
-    lds_col(gp - 288, gB); zB = lds_f64(xrow - xs + 8 * c);        // local stage i-1
-    sts_f64_if(act && i >= 0, xrow + 8 * c, oe_row_dot(gA, zA, a));
-    __syncwarp();
-    lds_row(xrow, a);
-    if (s + 1 >= cmax) break;
-    lds_col(gp - 576, gA); zA = lds_f64(xrow - 2 * xs + 8 * c);    // local stage i-2
-    sts_f64_if(act && i - 1 >= 0, xrow - xs + 8 * c, oe_row_dot(gB, zB, a));
-    __syncwarp();
-    lds_row(xrow - xs, a);
-    gp -= 576; xrow -= 2 * xs;
+  if (lane < 12) {
+    const bool bottom = lane >= 6;
+    const int c = bottom ? lane - 6 : lane;
+    const OEHalf h = oe_half(w, oe, bottom);
+    const int cmax = oe.jm > oe.nb ? oe.jm : oe.nb;
+    const int xs = h.xstep * 8;
+    int i = h.cnt - 1;                                               // local stage of this half at the current step (< 0: done)
+    unsigned xrow = smem_u32(h.x0) + xs * i;                         // row of local stage i
+    unsigned gp = smem_u32(h.g0) + 288 * i + 8 * c;                  // column c of the block of step i+1
+    double a[6], gA[6], gB[6], zA, zB;
+    lds_row(smem_u32(w.nx(2 * oe.jm)), a);                           // x_m
+    lds_col(gp, gA); zA = lds_f64(xrow + 8 * c);
+    for (int s = 0; s < cmax; s += 2, i -= 2) {
+      lds_col(gp - 288, gB); zB = lds_f64(xrow - xs + 8 * c);        // local stage i-1
+      sts_f64_if(i >= 0, xrow + 8 * c, oe_row_dot(gA, zA, a));
+      __syncwarp(MPC_ROW_LANES);
+      lds_row(xrow, a);
+      if (s + 1 >= cmax) break;
+      lds_col(gp - 576, gA); zA = lds_f64(xrow - 2 * xs + 8 * c);    // local stage i-2
+      sts_f64_if(i - 1 >= 0, xrow - xs + 8 * c, oe_row_dot(gB, zB, a));
+      __syncwarp(MPC_ROW_LANES);
+      lds_row(xrow - xs, a);
+      gp -= 576; xrow -= 2 * xs;
+    }
   }
+  __syncwarp();
 }
 
 __device__ __forceinline__ int next_problem_warp(int* counter, int lane) {
@@ -146,11 +159,72 @@ __device__ __forceinline__ int next_problem_warp(int* counter, int lane) {
 // sweeps / factorisation run in two lanes of ONE warp of the group, chosen so that the chain warps of the resident
 // groups spread over the four SM sub-partitions (warp w issues on sub-partition w % 4).
 // ------------------------------------------------------------------------------------------------
+#ifndef MPC_REG_STATE
+#define MPC_REG_STATE 0      // register form: 1 = stage state in registers inside a block, 0 = state stays in the records
+#endif
 struct GroupShared {
   int next;
   int anyv[2];
   double red[2][8];
+  IterConst ic;       // register form: the per-problem constants of a block of iterations (read from here inside the block)
 };
+
+// Register form (mpc_reg.h): a block of nb iterations of one problem by its two warps.  A real call (noinline): inside, the
+// only long-lived registers are the stage record of the lane - inlined into the driver, the driver's own state (settings,
+// residuals, pointers, counters) competed with it and the record was spilled to local memory, which with 227 KB of shared
+// memory carved out of the L1 means L2 round trips.  `ev`: this warp owns the even stages and runs the sweeps.
+template <int STATE>
+__device__ __noinline__ void reg_block_run(double* base, int N, int fpad, int xpad, double dt, const IterConst* csm, int nb,
+                                           int lane, int ev, int bar_id, unsigned long long* tags) {
+#ifdef MPC_TIMING     // dev builds: cycles of the parts of an iteration as the even warp's lane 0 sees them (tags 20..26)
+  long long tq = clock64(), tacc[7] = {0, 0, 0, 0, 0, 0, 0};
+#define MPC_BTAG(n) do { const long long now_ = clock64(); tacc[(n) - 20] += now_ - tq; tq = now_; } while (0)
+#else
+#define MPC_BTAG(n) do { } while (0)
+#endif
+  const View w{base, N, fpad, xpad};
+  const OEView oe = oe_view(w);
+  const volatile IterConst& c = *csm;          // read where used (see mpc_pair.h: pair_stage)
+  Params p;
+  p.dt = dt; p.N = N;
+  const int k = 2 * lane + (ev ? 0 : 1);
+  const bool on = k <= N;
+  StageRegs R;
+  StageTmp T;
+  if (on) reg_load<STATE>(w, k, R);
+#pragma unroll 1
+  for (int i = 0; i < nb; ++i) {
+    MPC_BTAG(26);
+    if (ev) {
+      oe_forward_lanes(lane, w, oe);
+      MPC_BTAG(20);
+      if (on) oe_diag_stage(w, oe, k);
+      __syncwarp();
+      MPC_BTAG(21);
+      oe_backward_lanes(lane, w, oe);
+      MPC_BTAG(22);
+    }
+    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // B_a: x~ of the even stages
+    if (!ev && on) reg_expand(w, p, c, oe, k, R, T);
+    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // B_b: x~ of the odd stages
+    MPC_BTAG(23);
+    if (ev && on) reg_gather_even(w, k, T);
+    if (on) reg_update<STATE>(w, p, c, k, R, T);
+    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // B_c: (d, G) of every stage
+    MPC_BTAG(24);
+    if (on) reg_rhs<STATE>(w, p, c, oe, k, R, T);
+    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // B_d: products of t_o
+    MPC_BTAG(25);
+    if (ev && on) reg_fixup(w, p, c, k, T);
+    if (ev) __syncwarp();
+  }
+#ifdef MPC_TIMING
+  if (ev && lane == 0 && tags) for (int q = 0; q < 7; ++q) atomicAdd(&tags[20 + q], (unsigned long long)tacc[q]);
+#endif
+  asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+  if (on) reg_store<STATE>(w, k, R);
+  asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+}
 
 template <int WPP>
 struct GroupExec {
@@ -253,6 +327,45 @@ struct GroupExec {
   __device__ __forceinline__ void oe_backward(const View& w, const OEView& oe) {
     if (chain_warp()) oe_backward_lanes(lane, w, oe);
     group_sync();
+  }
+  // ---- pair form of an iteration (mpc_pair.h): one lane per pair of stages, neighbours exchanged through shuffles.
+  // One warp per problem only (N + 1 <= 64).
+  __device__ __forceinline__ void pair_pass(const View& w, const Params& p, const IterConst& c, const OEView& oe) {
+    const unsigned full = 0xffffffffu;
+    const bool on = lane < pair_lanes(w.N);
+    PairCtx cx;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { cx.xo[j] = 0.0; cx.t[j] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cx.dd[j] = 0.0;
+    cx.Ge[3] = cx.Ge[4] = 0.0;
+    if (on) pair_expand(w, p, c, oe, lane, cx);
+    double ua = __shfl_up_sync(full, cx.xo[4], 1), ud = __shfl_up_sync(full, cx.xo[5], 1);
+    if (lane == 0) { ua = 0.0; ud = 0.0; }
+    if (on) pair_update(w, p, c, lane, cx, ua, ud);
+    double dprev[4], rnext[2], tprev[6];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) dprev[r] = __shfl_up_sync(full, cx.dd[r], 1);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) rnext[i] = __shfl_down_sync(full, cx.Ge[3 + i], 1);
+    if (on) pair_rhs(w, p, c, oe, lane, cx, dprev, rnext);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) tprev[j] = __shfl_up_sync(full, cx.t[j], 1);
+    if (on) pair_fixup(w, p, c, lane, cx, tprev);
+    group_sync();
+  }
+  // ---- register form of the iterations (mpc_reg.h): two warps per problem, the chain warp owns the even stages and runs
+  // the sweeps, the other warp the odd stages; lane j <-> stage 2j (+1).  nb iterations, then the records are written back.
+  __device__ __forceinline__ void admm_block(const View& w, const Params& p, const IterConst& c, const OEView&, int nb) {
+    static_assert(WPP == 2, "register form: two warps per problem");
+    if (gl() == 0) sh->ic = c;
+    group_sync();
+#ifdef MPC_TIMING
+    unsigned long long* tg = tags;
+#else
+    unsigned long long* tg = nullptr;
+#endif
+    reg_block_run<MPC_REG_STATE>(w.base, w.N, w.fpad, w.xpad, p.dt, &sh->ic, nb, lane, chain_warp() ? 1 : 0, 1 + grp(), tg);
   }
   __device__ __forceinline__ void factor(const View& w) {
     if (chain_warp()) factor_twisted_lanes(lane, w, 0, max(half_top(w.N), half_bot(w.N)), true);

@@ -21,7 +21,7 @@ struct BatchArgs {
 // K_solve: batched MPCController.solve.  The CTA holds P problems, each owned by a group of WPP warps (GroupExec).
 // <256,1>: P <= 8 one-warp groups, 255 registers; <128,2>: P <= 2 two-warp groups for long horizons.
 // ------------------------------------------------------------------------------------------------
-template <int MAXT, int WPP, bool SHORT>
+template <int MAXT, int WPP, int FORM>
 __global__ void __launch_bounds__(MAXT, 1) mpc_solve_kernel(Params p, Settings s, BatchArgs a, int P, int F) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(MAXT, 1) mpc_solve_kernel(Params p, Settings s
     io.status = a.status + b; io.iters = a.iters + b;
     io.pri_res = a.pri ? a.pri + b : nullptr; io.dua_res = a.dua ? a.dua + b : nullptr;
     io.info = a.info ? a.info + 4 * (size_t)b : nullptr;
-    solve_problem<SHORT>(ex, w, p, s, io);
+    solve_problem<FORM>(ex, w, p, s, io);
     ex.group_sync();
   }
 }
@@ -77,7 +77,7 @@ __device__ __forceinline__ void f_discrete_dev(const Params& p, const double* x,
 }
 
 // One vehicle, all steps (TrajectoryTracker.track loop body, control_stage.py:100-150), generic in the execution policy
-template <bool SHORT, class Exec>
+template <int FORM, class Exec>
 __device__ __forceinline__ void rollout_vehicle(Exec& ex, const View& w, const Params& p, const Settings& s,
                                                 const cudampc_rollout_cfg& cfg, const RolloutArgs& a, int b) {
   const int N = p.N;
@@ -114,7 +114,7 @@ __device__ __forceinline__ void rollout_vehicle(Exec& ex, const View& w, const P
     io.status = st_out; io.iters = it_out; io.pri_res = nullptr; io.dua_res = nullptr; io.info = nullptr;
     Settings ss = s;
     ss.warm_start = (s.warm_start && step > 0) ? 1 : 0;
-    solve_problem<SHORT>(ex, w, p, ss, io);
+    solve_problem<FORM>(ex, w, p, ss, io);
     ex.group_sync();
     int status = *st_out;
     if (status != STATUS_SOLVED && status != STATUS_SOLVED_INACCURATE && cfg.relax_on_failure) {
@@ -124,7 +124,7 @@ __device__ __forceinline__ void rollout_vehicle(Exec& ex, const View& w, const P
       pr.du_lo[1] -= cfg.relax_ddelta; pr.du_hi[1] += cfg.relax_ddelta;
       io.ref.vscale = cfg.relax_v_scale;
       ss.warm_start = 0;
-      solve_problem<SHORT>(ex, w, pr, ss, io);
+      solve_problem<FORM>(ex, w, pr, ss, io);
       ex.group_sync();
       status = *st_out;
       flags |= 4;
@@ -161,25 +161,25 @@ __device__ __forceinline__ void rollout_vehicle(Exec& ex, const View& w, const P
   ex.single([&]() { a.n_steps[b] = nst; a.flags[b] = flags; });
 }
 
-template <bool SHORT>
+template <int FORM>
 __global__ void __launch_bounds__(32) mpc_rollout_kernel(Params p, Settings s, cudampc_rollout_cfg cfg, RolloutArgs a) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;
   int fpad, xpad; layout_pads(p.N, fpad, xpad);
   View w{smem, p.N, fpad, xpad};
   GroupExec<1> ex{lane, 0, nullptr};
-  for (int b = ex.fetch(a.counter); b < a.batch; b = ex.fetch(a.counter)) rollout_vehicle<SHORT>(ex, w, p, s, cfg, a, b);
+  for (int b = ex.fetch(a.counter); b < a.batch; b = ex.fetch(a.counter)) rollout_vehicle<FORM>(ex, w, p, s, cfg, a, b);
 }
 
 
 // ------------------------------------------------------------------------------------------------
 // Instantiations and their launchers
 // ------------------------------------------------------------------------------------------------
-// K_solve: one warp per problem with the short form of the phases (N+1 <= 32) or the general form, two warps per problem
-// (general form, long horizons); K_rollout: one warp per vehicle, short or general form.
-enum SolveVariant { SOLVE_W1_SHORT = 0, SOLVE_W1 = 1, SOLVE_W2 = 2 };
+// K_solve: one warp per problem with the short (N+1 <= 32), pair (N+1 <= 64) or general form of the phases, two warps per
+// problem (general form, long horizons); K_rollout: one warp per vehicle, any of the three forms (mpc_solve.h FORM_*).
+enum SolveVariant { SOLVE_W1_SHORT = 0, SOLVE_W1 = 1, SOLVE_W2 = 2, SOLVE_W1_PAIR = 3, SOLVE_W2_REG = 4 };
 cudaError_t solve_set_smem(int variant, int bytes);
 void solve_launch(int variant, int grid, int threads, int smem, cudaStream_t st, const Params& p, const Settings& s, const BatchArgs& a, int P, int F);
-cudaError_t rollout_set_smem(bool short_form, int bytes);
-cudaError_t rollout_occupancy(bool short_form, int bytes, int* blocks_per_sm);
-void rollout_launch(bool short_form, int grid, int smem, cudaStream_t st, const Params& p, const Settings& s, const cudampc_rollout_cfg& cfg, const RolloutArgs& a);
+cudaError_t rollout_set_smem(int form, int bytes);
+cudaError_t rollout_occupancy(int form, int bytes, int* blocks_per_sm);
+void rollout_launch(int form, int grid, int smem, cudaStream_t st, const Params& p, const Settings& s, const cudampc_rollout_cfg& cfg, const RolloutArgs& a);

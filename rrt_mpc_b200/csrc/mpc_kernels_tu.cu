@@ -6,23 +6,29 @@
   void solve_launch_##n(int grid, int threads, int smem, cudaStream_t st, const Params& p, const Settings& s, const BatchArgs& a, int P, int F) { \
     mpc_solve_kernel<__VA_ARGS__><<<grid, threads, smem, st>>>(p, s, a, P, F);                                                \
   }
-#define ROLLOUT_TU(name, SHORT)                                                                                              \
-  cudaError_t rollout_set_smem_##name(int bytes) { return cudaFuncSetAttribute(mpc_rollout_kernel<SHORT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); } \
-  cudaError_t rollout_occupancy_##name(int bytes, int* n) { return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, mpc_rollout_kernel<SHORT>, 32, bytes); } \
+#define ROLLOUT_TU(name, FORM)                                                                                               \
+  cudaError_t rollout_set_smem_##name(int bytes) { return cudaFuncSetAttribute(mpc_rollout_kernel<FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); } \
+  cudaError_t rollout_occupancy_##name(int bytes, int* n) { return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, mpc_rollout_kernel<FORM>, 32, bytes); } \
   void rollout_launch_##name(int grid, int smem, cudaStream_t st, const Params& p, const Settings& s, const cudampc_rollout_cfg& cfg, const RolloutArgs& a) { \
-    mpc_rollout_kernel<SHORT><<<grid, 32, smem, st>>>(p, s, cfg, a);                                                          \
+    mpc_rollout_kernel<FORM><<<grid, 32, smem, st>>>(p, s, cfg, a);                                                          \
   }
 
 #if MPC_TU == 0
-SOLVE_TU(0, 256, 1, true)
+SOLVE_TU(0, 256, 1, FORM_SHORT)
 #elif MPC_TU == 1
-SOLVE_TU(1, 256, 1, false)
+SOLVE_TU(1, 256, 1, FORM_GENERAL)
 #elif MPC_TU == 2
-SOLVE_TU(2, 128, 2, false)
+SOLVE_TU(2, 128, 2, FORM_GENERAL)
 #elif MPC_TU == 3
-ROLLOUT_TU(short, true)
+ROLLOUT_TU(short, FORM_SHORT)
 #elif MPC_TU == 4
-ROLLOUT_TU(general, false)
+ROLLOUT_TU(general, FORM_GENERAL)
+#elif MPC_TU == 5
+SOLVE_TU(3, 256, 1, FORM_PAIR)
+#elif MPC_TU == 6
+ROLLOUT_TU(pair, FORM_PAIR)
+#elif MPC_TU == 7
+SOLVE_TU(4, 256, 2, FORM_REG)
 #else
-#error "MPC_TU must be 0..4"
+#error "MPC_TU must be 0..7"
 #endif

@@ -41,9 +41,13 @@ MPC_HD Residuals compute_residuals(Exec& ex, const View& w, const Params& p, con
   return o;
 }
 
-// SHORT: form of the ADMM phases for horizons with N+1 <= 32 (one lane per stage; mpc_core.h admm_rhs_stage_short);
-// the general form runs the phases one parity of stages at a time.  Separate instantiations, so a kernel carries one form.
-template <bool SHORT, class Exec>
+// FORM of the ADMM phases.  FORM_GENERAL: one parity of stages at a time (any horizon, any number of warps per problem);
+// FORM_SHORT: horizons with N+1 <= 32, one lane per stage (mpc_core.h admm_rhs_stage_short); FORM_PAIR: horizons with
+// N+1 <= 64, one lane per pair of stages, update and next right-hand side in ONE pass (mpc_pair.h); FORM_REG: N+1 <= 64, two
+// warps per problem, every stage record in the registers of its lane for a block of iterations (mpc_reg.h).  Separate
+// instantiations, so a kernel carries one form.
+enum { FORM_GENERAL = 0, FORM_SHORT = 1, FORM_PAIR = 2, FORM_REG = 3 };
+template <int FORM, class Exec>
 MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settings& s, const ProblemIO& io) {
   const int N = w.N;
   const int NS = N + 1;
@@ -79,7 +83,7 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
   Mode mode = admm_mode(rho, s);
   IterConst ic = iter_const(w, p, s, rho);
   const OEView oe = oe_view(w);            // odd-even block solve of the ADMM iterations (mpc_oe.h)
-  bool need_factor = true;
+  bool need_factor = true, need_rhs = true;
 
   // ---- ADMM + polish --------------------------------------------------------------------------
   // OSQP: iterate until the residual test passes, then polish once.  Two opt-in extensions:
@@ -225,14 +229,35 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
       ex.tag(5); ex.oe_factor(w, p, mode, oe); ++n_fac;
       ic = iter_const(w, p, s, rho);
       need_factor = false;
+      need_rhs = true;
+    }
+    if constexpr (FORM == FORM_REG) {
+      // a block of iterations up to the next event (termination check, rho adaptation, iteration limit) with the stage
+      // records in registers; the first right-hand side after a (re)factorisation comes from the general parity passes
+      if (need_rhs) {
+        ex.tag(6);
+#pragma unroll 1
+        for (int par = 1; par >= 0; --par) ex.stages_par(NS, par, [&](int k) { admm_rhs_stage_oe(w, p, ic, oe, k); });
+        need_rhs = false;
+      }
+      int nb = s.max_iter - it;
+      if (s.check_termination > 0) { const int n = s.check_termination - it % s.check_termination; if (n < nb) nb = n; }
+      if (s.adaptive_rho && s.adaptive_rho_interval > 0) { const int n = s.adaptive_rho_interval - it % s.adaptive_rho_interval; if (n < nb) nb = n; }
+      if (nb < 1) nb = 1;
+      ex.tag(2);
+      ex.admm_block(w, p, ic, oe, nb);
+      it += nb; n_solve += nb;
+      after_update();
+      continue;
     }
     ex.tag(6);
-    if constexpr (SHORT) {
+    if constexpr (FORM == FORM_SHORT) {
       ex.stages(NS, [&](int k) { admm_rhs_stage_short(w, p, ic, oe, k); });
       ex.stages_par(NS, 0, [&](int k) { oe_even_fixup(w, p, ic, k); });
-    } else {
+    } else if (FORM != FORM_PAIR || need_rhs) {      // pair form: only the first right-hand side after a (re)factorisation
 #pragma unroll 1
       for (int par = 1; par >= 0; --par) ex.stages_par(NS, par, [&](int k) { admm_rhs_stage_oe(w, p, ic, oe, k); });
+      need_rhs = false;
     }
     ++it;
     ex.tag(16);
@@ -242,7 +267,9 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
     ex.tag(18);
     ex.oe_backward(w, oe); ++n_solve;
     ex.tag(2);
-    if constexpr (SHORT) {
+    if constexpr (FORM == FORM_PAIR) {
+      ex.pair_pass(w, p, ic, oe);          // update of this iteration + right-hand side of the next one
+    } else if constexpr (FORM == FORM_SHORT) {
       ex.stages_par(NS, 1, [&](int k) { oe_expand_odd(w, p, ic, oe, k); });
       ex.stages(NS, [&](int k) { admm_update_stage_short(w, p, ic, k); });
     } else {

@@ -9,6 +9,8 @@
 
 using namespace mpc;
 
+static int g_reg_state = 1;   // register form: 1 = stage state in per-stage copies (registers), 0 = left in the records
+
 struct EmuExec {
   int reverse;
   void tag(int) {}
@@ -40,6 +42,18 @@ struct EmuExec {
     if (!reverse) { oe_factor_half(oe_half(w, oe, false), Ut); oe_factor_half(oe_half(w, oe, true), Ub); }
     else { oe_factor_half(oe_half(w, oe, true), Ub); oe_factor_half(oe_half(w, oe, false), Ut); }
     oe_factor_middle(oe, Ut, Ub);
+  }
+  // pair form of an iteration: the parts of mpc_pair.h lane after lane (in either order), neighbours' values from their contexts
+  void pair_pass(const View& w, const Params& p, const IterConst& c, const OEView& oe) {
+    std::vector<PairCtx> cx(pair_lanes(w.N));
+    pair_pass_seq(w, p, c, oe, cx.data(), reverse != 0);
+  }
+  // register form: a block of iterations on per-stage copies of the records
+  void admm_block(const View& w, const Params& p, const IterConst& c, const OEView& oe, int nb) {
+    std::vector<StageRegs> R(w.N + 1);
+    std::vector<StageTmp> T(w.N + 1);
+    if (g_reg_state) reg_block_seq<1>(w, p, c, oe, nb, R.data(), T.data(), reverse != 0);
+    else reg_block_seq<0>(w, p, c, oe, nb, R.data(), T.data(), reverse != 0);
   }
   void oe_forward(const View& w, const OEView&) { oe_forward_seq(w); }
   void oe_backward(const View& w, const OEView&) { oe_backward_seq(w); }
@@ -76,8 +90,8 @@ static void unpack(const double* par, const double* set, int N, Params& p, Setti
   s.warm_start = (int)set[i++]; s.polish_retry = (int)set[i++]; s.early_polish = (int)set[i++]; s.early_polish_start = (int)set[i++];
 }
 
-static int g_form = -1;      // -1: what the library picks (short form for N+1 <= 32), 0: general form, 1: short form
-void emu_set_form(int f) { g_form = f; }
+static int g_form = -1;      // -1: what the library picks (short form for N+1 <= 32, pair form for N+1 <= 64), else FORM_* of mpc_solve.h
+void emu_set_form(int f) { g_form = f & 3; g_reg_state = (f & 4) ? 0 : 1; if (f < 0) { g_form = -1; g_reg_state = 1; } }
 
 int emu_solve_batch(const double* par, const double* set, int N, int B, int reverse,
                     const double* x0, const double* ref, const double* u_prev, double* warm,
@@ -96,7 +110,11 @@ int emu_solve_batch(const double* par, const double* set, int N, int B, int reve
     Settings sb = s;
     if (!warm) sb.warm_start = 0;
     EmuExec ex{reverse};
-    if (g_form == 1 || (g_form < 0 && N + 1 <= 32)) solve_problem<true>(ex, w, p, sb, io); else solve_problem<false>(ex, w, p, sb, io);
+    const int form = g_form >= 0 ? g_form : (N + 1 <= 32 ? FORM_SHORT : (N + 1 <= 64 ? FORM_PAIR : FORM_GENERAL));
+    if (form == FORM_SHORT && N + 1 <= 32) solve_problem<FORM_SHORT>(ex, w, p, sb, io);
+    else if (form == FORM_PAIR && N + 1 <= 64) solve_problem<FORM_PAIR>(ex, w, p, sb, io);
+    else if (form == FORM_REG && N + 1 <= 64) solve_problem<FORM_REG>(ex, w, p, sb, io);
+    else solve_problem<FORM_GENERAL>(ex, w, p, sb, io);
   }
   return 0;
 }

@@ -193,3 +193,30 @@ def test_short_and_general_form_of_the_phases_agree():
     for k in ("u0", "Xp", "Up", "iters", "status"):
         assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], ar[k])
     assert np.abs(a["u0"] - g["n20_u0"][:nb]).max() < 1e-8
+
+
+@pytest.mark.parametrize("N,du", [(50, 0.02), (20, 0.15), (15, 0.15), (33, 0.05), (63, 0.05), (2, 0.15), (1, 0.15)])
+@pytest.mark.parametrize("form", [2, 3, 7])
+def test_pair_and_general_form_of_the_phases_agree(N, du, form):
+    """Horizons with N+1 <= 64 run an iteration as ONE pass with a lane per pair of stages (mpc_pair.h: update of iteration
+    i and right-hand side of iteration i+1 fused, neighbours' values exchanged between lanes).  Every sum has the operands
+    and the order of the general parity form, so the iterates agree to the last bit; the lanes of a part may run in either
+    order (what a warp does concurrently).  Even / odd N: the terminal stage is the even / the odd stage of the last lane.
+    Form 3 (mpc_reg.h) keeps every stage record in the registers of one lane for a block of iterations, form 7 is the same
+    two-warp schedule with the state left in the records: same arithmetic again."""
+    from rrt_mpc_b200.synthetic import make_batch
+    p = oracle_params(N, du)
+    nb = 4
+    x0, ref, up = make_batch(nb, N, seed=11)
+    kw = dict(polish_passes=5, polish_retry=2, early_polish=1, **TIGHT)
+    try:
+        E.set_form(form)
+        a = E.solve(p, x0, ref, up, **kw)
+        ar = E.solve(p, x0, ref, up, reverse=1, **kw)
+        E.set_form(0)
+        b = E.solve(p, x0, ref, up, **kw)
+    finally:
+        E.set_form(-1)
+    assert (a["status"] == 1).all()
+    for k in ("u0", "Xp", "Up", "iters", "status", "info"):
+        assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], ar[k]), k

@@ -3,6 +3,8 @@ import sys, dataclasses, os
 import numpy as np
 sys.path.insert(0, ".")
 import torch
+import rrt_mpc_b200._lib as _L
+if os.environ.get('CUDAMPC_LIB'): _L.LIB_PATH = os.path.abspath(os.environ['CUDAMPC_LIB'])
 from rrt_mpc_b200 import MPCController, SolverSettings, MPCConfig
 from rrt_mpc_b200.synthetic import make_batch
 N, B = int(sys.argv[1]), int(sys.argv[2]); eps = float(sys.argv[3]) if len(sys.argv) > 3 else 1e-6
@@ -21,7 +23,9 @@ for _ in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); r = ctl.solve_batch(dx0, dref, u_prev=dup); e1.record(); torch.cuda.synchronize()
     best = min(best, e0.elapsed_time(e1))
+import subprocess
+clk = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw,clocks_event_reasons.active", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip()
 it = r.iters.double().mean().item()
 cyc = best * 1e-3 / (B * it) * 148 * 1.8e9
 print(f"[{" ".join(k[4:].lower()+"="+v for k,v in os.environ.items() if k.startswith("SET_")) or "default"}] N={N} B={B} per_sm={ctl.problems_per_sm()}: {best:.2f} ms -> {B/best*1e3:.0f} solves/s, mean iters {it:.1f}, "
-      f"{cyc:.0f} SM-cycles per problem-iteration, solved {(r.status==1).sum().item()}")
+      f"{cyc:.0f} SM-cycles per problem-iteration, solved {(r.status==1).sum().item()} | {clk}")

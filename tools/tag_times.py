@@ -29,7 +29,8 @@ r = ctl.solve_batch(dx0, dref, u_prev=dup); torch.cuda.synchronize()
 lib.cudampc_debug_tag_cycles(ctl._handle(1).ptr, out, 1)
 names = ["setup", "-", "update (odd: expand + A1, even: A1)", "residuals/check", "-", "factor (ADMM)", "rhs (odd: A2 + t, even: A2 + b')", "final/outputs",
          "save iterate", "polish: activity+assemble", "polish: factor", "polish: 4x(rhs, solve, dual, primal)", "polish: residuals+decision",
-         "resume: load+assemble", "resume: factor", "early probe", "sweep forward + middle", "diagonal step", "sweep backward"] + ["-"] * 13
+         "resume: load+assemble", "resume: factor", "early probe", "sweep forward + middle", "diagonal step", "sweep backward", "-",
+         "  block: forward", "  block: diagonal", "  block: backward", "  block: B_a, expand (odd), B_b", "  block: update (A1 + own A2), B_c", "  block: rhs (+ t_o), B_d", "  block: fixup"] + ["-"] * 5
 v = np.array(list(out), dtype=np.float64); it = r.iters.double().mean().item(); info = r.info.double().mean(0).cpu().numpy()
 print(f"N={N} B={B} early={early}: mean iters {it:.1f}, factorisations {info[1]:.2f}, solves {info[3]:.1f}, total {v.sum()/B/1e3:.0f} k cycles per problem")
 for n, c in sorted(zip(names, v), key=lambda t: -t[1]):
