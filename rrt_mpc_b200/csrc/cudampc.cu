@@ -187,6 +187,7 @@ void solve_launch_1(int, int, int, cudaStream_t, const Params&, const Settings&,
 void solve_launch_2(int, int, int, cudaStream_t, const Params&, const Settings&, const BatchArgs&, int, int);
 void solve_launch_3(int, int, int, cudaStream_t, const Params&, const Settings&, const BatchArgs&, int, int);
 void solve_launch_4(int, int, int, cudaStream_t, const Params&, const Settings&, const BatchArgs&, int, int);
+int solve_reg_max_threads();
 cudaError_t rollout_set_smem_short(int), rollout_set_smem_general(int), rollout_set_smem_pair(int);
 cudaError_t rollout_occupancy_short(int, int*), rollout_occupancy_general(int, int*), rollout_occupancy_pair(int, int*);
 void rollout_launch_short(int, int, cudaStream_t, const Params&, const Settings&, const cudampc_rollout_cfg&, const RolloutArgs&);
@@ -385,8 +386,9 @@ int cudampc_create(const cudampc_params* params, int max_batch, int device, cuda
     h->grp_wpp = (P <= 2 && p.N + 1 > 32) ? 2 : 1;
     if (const char* we = getenv("CUDAMPC_WPP")) { int v = atoi(we); if (v == 1 || (v == 2 && P <= 2)) h->grp_wpp = v; }
     h->variant = h->grp_wpp == 2 ? SOLVE_W2 : (h->form == FORM_SHORT ? SOLVE_W1_SHORT : h->form == FORM_PAIR ? SOLVE_W1_PAIR : SOLVE_W1);
-    // register form (mpc_reg.h): two warps per problem, at most 4 problems (8 warps x 255 registers; more warps would cap the registers at 168)
-    if (solve_form == FORM_REG) { if (P > 4) { P = 4; h->grp_P = 4; } h->grp_wpp = 2; h->variant = SOLVE_W2_REG; }
+    // register form (mpc_reg.h): two warps per problem, as many problems as the kernel was compiled for (256 threads: 255
+    // registers; more: 168 registers)
+    if (solve_form == FORM_REG) { const int pm = solve_reg_max_threads() / 64; if (P > pm) { P = pm; h->grp_P = pm; } h->grp_wpp = 2; h->variant = SOLVE_W2_REG; }
     h->grp_smem = P * (F * (int)sizeof(double) + (int)sizeof(GroupShared)) + 16;
     e = solve_set_smem(h->variant, h->grp_smem);
     if (e != cudaSuccess) { delete h; return fail(nullptr, CUDAMPC_ERR_CUDA, "CUDA failure: %s", cudaGetErrorString(e)); }

@@ -159,22 +159,20 @@ __device__ __forceinline__ int next_problem_warp(int* counter, int lane) {
 // sweeps / factorisation run in two lanes of ONE warp of the group, chosen so that the chain warps of the resident
 // groups spread over the four SM sub-partitions (warp w issues on sub-partition w % 4).
 // ------------------------------------------------------------------------------------------------
-#ifndef MPC_REG_STATE
-#define MPC_REG_STATE 0      // register form: 1 = stage state in registers inside a block, 0 = state stays in the records
-#endif
 struct GroupShared {
   int next;
   int anyv[2];
   double red[2][8];
-  IterConst ic;       // register form: the per-problem constants of a block of iterations (read from here inside the block)
+  Drv drv;            // register form: the driver's state between its pieces (mpc_drv.h); drv.ic is read inside the blocks
 };
 
-// Register form (mpc_reg.h): a block of nb iterations of one problem by its two warps.  A real call (noinline): inside, the
-// only long-lived registers are the stage record of the lane - inlined into the driver, the driver's own state (settings,
-// residuals, pointers, counters) competed with it and the record was spilled to local memory, which with 227 KB of shared
-// memory carved out of the L1 means L2 round trips.  `ev`: this warp owns the even stages and runs the sweeps.
+// Register form (mpc_reg.h): a block of nb iterations of one problem by its two warps.  Meant to be inlined at the TOP LEVEL
+// of the kernel (mpc_kernels.cuh: mpc_solve_reg_kernel), where nothing else is alive: there the stage record, the
+// temporaries of the fused pass and the sweeps fit the 255 registers without a spill (250 used).  Inlined into the driver,
+// or as a real call (callee-saved registers of the ABI), ptxas parks part of the record in local memory, which with 227 KB
+// of shared memory carved out of the L1 is slow.  `ev`: this warp owns the even stages and runs the sweeps.
 template <int STATE>
-__device__ __noinline__ void reg_block_run(double* base, int N, int fpad, int xpad, double dt, const IterConst* csm, int nb,
+__device__ __forceinline__ void reg_block_run(double* base, int N, int fpad, int xpad, double dt, const IterConst* csm, int nb,
                                            int lane, int ev, int bar_id, unsigned long long* tags) {
 #ifdef MPC_TIMING     // dev builds: cycles of the parts of an iteration as the even warp's lane 0 sees them (tags 20..26)
   long long tq = clock64(), tacc[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -189,9 +187,22 @@ __device__ __noinline__ void reg_block_run(double* base, int N, int fpad, int xp
   p.dt = dt; p.N = N;
   const int k = 2 * lane + (ev ? 0 : 1);
   const bool on = k <= N;
+  // every word defined here: a register that is read without a definition on some path (the lanes beyond the horizon) is
+  // live from the kernel's entry, i.e. across the driver's code as well
   StageRegs R;
   StageTmp T;
+#pragma unroll
+  for (int j = 0; j < SR; ++j) R.r[j] = 0.0;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) { T.xt[j] = 0.0; T.xn[j] = 0.0; T.b[j] = 0.0; }
+#pragma unroll
+  for (int j = 0; j < 5; ++j) T.G[j] = 0.0;
+  T.ua = 0.0; T.ud = 0.0;
   if (on) reg_load<STATE>(w, k, R);
+  // One loop for both warp roles: the update and the right-hand side are ONE copy of code shared by the two warps (two
+  // loops - one per role - measured slower with early polish: the iteration loop competes for the 32 KB instruction cache
+  // with the polish code other resident problems run).
+#define MPC_BAR() asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory")
 #pragma unroll 1
   for (int i = 0; i < nb; ++i) {
     MPC_BTAG(26);
@@ -204,16 +215,16 @@ __device__ __noinline__ void reg_block_run(double* base, int N, int fpad, int xp
       oe_backward_lanes(lane, w, oe);
       MPC_BTAG(22);
     }
-    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // B_a: x~ of the even stages
+    MPC_BAR();                                        // B_a: x~ of the even stages
     if (!ev && on) reg_expand(w, p, c, oe, k, R, T);
-    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // B_b: x~ of the odd stages
+    MPC_BAR();                                        // B_b: x~ of the odd stages
     MPC_BTAG(23);
     if (ev && on) reg_gather_even(w, k, T);
     if (on) reg_update<STATE>(w, p, c, k, R, T);
-    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // B_c: (d, G) of every stage
+    MPC_BAR();                                        // B_c: (d, G) of every stage
     MPC_BTAG(24);
     if (on) reg_rhs<STATE>(w, p, c, oe, k, R, T);
-    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // B_d: products of t_o
+    MPC_BAR();                                        // B_d: t_o
     MPC_BTAG(25);
     if (ev && on) reg_fixup(w, p, c, k, T);
     if (ev) __syncwarp();
@@ -357,15 +368,15 @@ struct GroupExec {
   // ---- register form of the iterations (mpc_reg.h): two warps per problem, the chain warp owns the even stages and runs
   // the sweeps, the other warp the odd stages; lane j <-> stage 2j (+1).  nb iterations, then the records are written back.
   __device__ __forceinline__ void admm_block(const View& w, const Params& p, const IterConst& c, const OEView&, int nb) {
-    static_assert(WPP == 2, "register form: two warps per problem");
-    if (gl() == 0) sh->ic = c;
+    static_assert(WPP == 2, "register form: two warps per problem");     // generic path (state in the records); the product kernel is mpc_solve_reg_kernel
+    if (gl() == 0) sh->drv.ic = c;
     group_sync();
 #ifdef MPC_TIMING
     unsigned long long* tg = tags;
 #else
     unsigned long long* tg = nullptr;
 #endif
-    reg_block_run<MPC_REG_STATE>(w.base, w.N, w.fpad, w.xpad, p.dt, &sh->ic, nb, lane, chain_warp() ? 1 : 0, 1 + grp(), tg);
+    reg_block_run<0>(w.base, w.N, w.fpad, w.xpad, p.dt, &sh->drv.ic, nb, lane, chain_warp() ? 1 : 0, 1 + grp(), tg);
   }
   __device__ __forceinline__ void factor(const View& w) {
     if (chain_warp()) factor_twisted_lanes(lane, w, 0, max(half_top(w.N), half_bot(w.N)), true);

@@ -52,6 +52,93 @@ __global__ void __launch_bounds__(MAXT, 1) mpc_solve_kernel(Params p, Settings s
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K_solve, register form (mpc_reg.h, mpc_drv.h): two warps per problem; the iteration blocks are inlined HERE, at the top
+// level of the kernel, and everything else of the driver runs in three real calls that keep their state in shared memory.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ ProblemIO batch_io(const BatchArgs& a, int b, int N) {
+  const int ws = warm_size(N);
+  ProblemIO io;
+  io.x0 = a.x0 + 4 * (size_t)b;
+  io.ref = RefWin{a.ref + (size_t)4 * (N + 1) * b, 0, N + 1, 1.0};
+  io.u_prev = a.u_prev ? a.u_prev + 2 * (size_t)b : nullptr;
+  io.warm = a.warm + (size_t)ws * b;
+  io.scratch = a.scratch + (size_t)ws * b;
+  io.u0 = a.u0 + 2 * (size_t)b;
+  io.Xp = a.Xp + (size_t)4 * (N + 1) * b;
+  io.Up = a.Up + (size_t)2 * N * b;
+  io.status = a.status + b; io.iters = a.iters + b;
+  io.pri_res = a.pri ? a.pri + b : nullptr; io.dua_res = a.dua ? a.dua + b : nullptr;
+  io.info = a.info ? a.info + 4 * (size_t)b : nullptr;
+  return io;
+}
+struct RegCtx { const Params* p; const Settings* s; const BatchArgs* a; double* base; GroupShared* sh; int N, fpad, xpad, lane, warp; };
+__device__ __forceinline__ GroupExec<2> reg_exec(const RegCtx& c) {
+  GroupExec<2> ex{c.lane, c.warp, c.sh};
+#ifdef MPC_TIMING
+  ex.tags = c.a->tags;
+#endif
+  return ex;
+}
+__device__ __forceinline__ void reg_drv_begin(RegCtx c, int b) {
+  const View w{c.base, c.N, c.fpad, c.xpad};
+  GroupExec<2> ex = reg_exec(c);
+  const ProblemIO io = batch_io(*c.a, b, c.N);
+  Drv d;
+  drv_begin(ex, w, *c.p, *c.s, io, d);
+  drv_prepare(ex, w, *c.p, *c.s, d);
+  if (ex.gl() == 0) c.sh->drv = d;
+  ex.group_sync();
+}
+__device__ __forceinline__ void reg_drv_after(RegCtx c, int b) {
+  const View w{c.base, c.N, c.fpad, c.xpad};
+  GroupExec<2> ex = reg_exec(c);
+  const ProblemIO io = batch_io(*c.a, b, c.N);
+  Drv d = c.sh->drv;
+  ex.group_sync();                          // every lane has its copy before lane 0 writes the new one
+  drv_after(ex, w, *c.p, *c.s, io, d);
+  if (!d.finished) drv_prepare(ex, w, *c.p, *c.s, d);
+  if (ex.gl() == 0) c.sh->drv = d;
+  ex.group_sync();
+}
+__device__ __forceinline__ void reg_drv_finish(RegCtx c, int b) {
+  const View w{c.base, c.N, c.fpad, c.xpad};
+  GroupExec<2> ex = reg_exec(c);
+  const ProblemIO io = batch_io(*c.a, b, c.N);
+  const Drv d = c.sh->drv;
+  drv_finish(ex, w, io, d);
+  ex.group_sync();
+}
+template <int MAXT, int STATE>
+__global__ void __launch_bounds__(MAXT, 1) mpc_solve_reg_kernel(const __grid_constant__ Params p, const __grid_constant__ Settings s,
+                                                                const __grid_constant__ BatchArgs a, int P, int F) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int N = p.N;
+  GroupShared* sh = reinterpret_cast<GroupShared*>(smem + (size_t)P * F) + warp / 2;
+  int fpad, xpad; layout_pads(N, fpad, xpad);
+  double* base = smem + (size_t)(warp / 2) * F;
+  GroupExec<2> ex{lane, warp, sh};
+  const int ev = ex.chain_warp() ? 1 : 0, bar_id = 1 + ex.grp();
+#ifdef MPC_TIMING
+  unsigned long long* tg = a.tags;
+#else
+  unsigned long long* tg = nullptr;
+#endif
+  for (int b = ex.fetch(a.counter); b < a.batch; b = ex.fetch(a.counter)) {
+    // The pieces of the driver are inlined; none of their values is alive across a block (Drv lives in shared memory
+    // between them).
+    const RegCtx c{&p, &s, &a, base, sh, N, fpad, xpad, lane, warp};
+    reg_drv_begin(c, b);
+    while (!*(volatile int*)&sh->drv.finished) {
+      const int nb = *(volatile int*)&sh->drv.nb;
+      reg_block_run<STATE>(base, N, fpad, xpad, p.dt, &sh->drv.ic, nb, lane, ev, bar_id, tg);
+      reg_drv_after(c, b);
+    }
+    reg_drv_finish(c, b);
+  }
+}
+
 __device__ __forceinline__ void f_discrete_vals(double dt, double L, const double* x, const double* u, double* out) {
   // vehicle_model.py:11-21 (beta = 0.0 is added to the yaw there)
   const double yaw = x[2], v = x[3];

@@ -69,8 +69,10 @@ MPC_HD void pair_expand(const View& w, const Params& p, const IterConst& c, cons
 // where they are used (volatile: one load per use, never hoisted into long-lived registers); multi-use scalars are copied
 // to locals first.
 template <class C>
-MPC_HD void pair_stage(const double* __restrict__ in, double* __restrict__ out, const double* cst, double* hdr, const Params& p, const C& c, int N, int k,
-                       const double* xt, const double* xn, double ua, double ud, double* G) {
+// (inx, outx): where the x / u entries (R_XU) and the dynamics duals (R_YE) are read and written - the same record as
+// (in, out) or, in the register form with partial residency, the shared-memory record while (in, out) is the register copy.
+MPC_HD void pair_stage(const double* __restrict__ in, double* __restrict__ out, const double* inx, double* outx, const double* cst, double* hdr,
+                       const Params& p, const C& c, int N, int k, const double* xt, const double* xn, double ua, double ud, double* G) {
   const bool reg = k < N;
   const double c_ra = c.ra, c_alpha = c.alpha, c_rho = c.rho, c_sigma = c.sigma;
   if (reg) {
@@ -79,10 +81,10 @@ MPC_HD void pair_stage(const double* __restrict__ in, double* __restrict__ out, 
     const double z1 = xn[1] - (xt[1] + lin[2] * xt[2] + lin[3] * xt[3]);
     const double z2 = xn[2] - (xt[2] + lin[4] * xt[5]);
     const double z3 = xn[3] - (xt[3] + p.dt * xt[4]);
-    out[R_YE + 0] = fma(c_ra, z0 - lin[5], in[R_YE + 0]);
-    out[R_YE + 1] = fma(c_ra, z1 - lin[6], in[R_YE + 1]);
-    out[R_YE + 2] = fma(c_ra, z2, in[R_YE + 2]);
-    out[R_YE + 3] = fma(c_ra, z3, in[R_YE + 3]);
+    outx[R_YE + 0] = fma(c_ra, z0 - lin[5], inx[R_YE + 0]);
+    outx[R_YE + 1] = fma(c_ra, z1 - lin[6], inx[R_YE + 1]);
+    outx[R_YE + 2] = fma(c_ra, z2, inx[R_YE + 2]);
+    outx[R_YE + 3] = fma(c_ra, z3, inx[R_YE + 3]);
   }
   if (k == 0) {
 #pragma unroll
@@ -113,7 +115,7 @@ MPC_HD void pair_stage(const double* __restrict__ in, double* __restrict__ out, 
   }
 #pragma unroll
   for (int j = 0; j < 6; ++j)
-    if (j < 4 || reg) { const double xo = in[R_XU + j]; out[R_XU + j] = fma(c_alpha, xt[j] - xo, xo); }
+    if (j < 4 || reg) { const double xo = inx[R_XU + j]; outx[R_XU + j] = fma(c_alpha, xt[j] - xo, xo); }
 }
 // d = rho_eq c - y of the dynamics rows of stage k (zeros for the terminal stage), from the state `st`
 template <class C>
@@ -137,12 +139,12 @@ MPC_HD void pair_update(const View& w, const Params& p, const IterConst& c, int 
   const int N = w.N, e = 2 * l, o = e + 1;
   const bool ib = e > 0 && e < N;
   double* re = w.rec(e);
-  pair_stage(re, re, re, w.hdr(), p, c, N, e, cx.xe, cx.xo, ib ? ua : 0.0, ib ? ud : 0.0, cx.Ge);
+  pair_stage(re, re, re, re, re, w.hdr(), p, c, N, e, cx.xe, cx.xo, ib ? ua : 0.0, ib ? ud : 0.0, cx.Ge);
   stage_d(re, re, c, e < N, cx.de);
   stage_base(re, re, c, e < N, cx.be);
   if (o <= N) {
     double* ro = w.rec(o);
-    pair_stage(ro, ro, ro, w.hdr(), p, c, N, o, cx.xo, cx.xn, o < N ? cx.xe[4] : 0.0, o < N ? cx.xe[5] : 0.0, cx.Go);
+    pair_stage(ro, ro, ro, ro, ro, w.hdr(), p, c, N, o, cx.xo, cx.xn, o < N ? cx.xe[4] : 0.0, o < N ? cx.xe[5] : 0.0, cx.Go);
     stage_d(ro, ro, c, o < N, cx.dd);
     stage_base(ro, ro, c, o < N, cx.bo);
   } else {

@@ -27,7 +27,6 @@ namespace mpc {
 struct StageRegs {
   double r[SR];        // the stage record, same layout as in shared memory; only the state (R_XU .. R_YE) and s-tilde (R_ST)
                        // live here - the constants (R_LIN, R_Q) are read from the record where they are used
-  double t[6];         // odd stages: t_o
 };
 // what a lane carries from one part of an iteration to the next
 struct StageTmp {
@@ -39,19 +38,17 @@ struct StageTmp {
 
 MPC_HD double* reg_mb(const View& w, int k) { return w.rec(k) + R_ST; }          // 6 doubles (R_ST[5] + pad)
 
-// STATE = 1: the ADMM state of the stage lives in R.r for the block; STATE = 0: it stays in the record (only t_o is carried)
+// STATE = 1: the ADMM state of the stage lives in R.r for the block; STATE = 2: only the row states and slacks (v, s,
+// s-tilde: 25 of the 35 doubles) do, x / u and the dynamics duals stay in the record; STATE = 0: everything stays in the record
 template <int STATE>
 MPC_HD void reg_load(const View& w, int k, StageRegs& R) {
   const double* rc = w.rec(k);
   if (STATE) {
 #pragma unroll
-  for (int j = 0; j < R_LIN; ++j) R.r[j] = rc[j];
+  for (int j = (STATE == 2 ? R_S : 0); j < (STATE == 2 ? R_YE : R_LIN); ++j) R.r[j] = rc[j];
 #pragma unroll
   for (int j = 0; j < 5; ++j) R.r[R_ST + j] = rc[R_ST + j];
   }
-#pragma unroll
-  for (int j = 0; j < 6; ++j) R.t[j] = 0.0;
-  if (k & 1) row_load(w.nx(k), R.t);
 }
 // state + s-tilde back to the record, t_o back to its row (the constants never change)
 template <int STATE>
@@ -59,11 +56,10 @@ MPC_HD void reg_store(const View& w, int k, const StageRegs& R) {
   double* rc = w.rec(k);
   if (STATE) {
 #pragma unroll
-  for (int j = 0; j < R_LIN; ++j) rc[j] = R.r[j];
+  for (int j = (STATE == 2 ? R_S : 0); j < (STATE == 2 ? R_YE : R_LIN); ++j) rc[j] = R.r[j];
 #pragma unroll
   for (int j = 0; j < 5; ++j) rc[R_ST + j] = R.r[R_ST + j];
   }
-  if (k & 1) row_store(w.nx(k), R.t);
 }
 
 // T1, odd k: x~ of the stage from the even neighbours' rows
@@ -84,8 +80,10 @@ MPC_HD void reg_expand(const View& w, const Params& p, const C& c, const OEView&
   }
   sym_load(oe.dinv + OE_SYM * (k >> 1), di);
   symv6(di, v, u);
+  double t[6];
+  row_load(w.nx(k), t);                    // t_o, published in this row by the last right-hand side
 #pragma unroll
-  for (int j = 0; j < 6; ++j) T.xt[j] = R.t[j] - u[j];
+  for (int j = 0; j < 6; ++j) T.xt[j] = t[j] - u[j];
   T.ua = k < N ? xp[4] : 0.0; T.ud = k < N ? xp[5] : 0.0;
   row_store(w.nx(k), T.xt);
 }
@@ -103,10 +101,11 @@ MPC_HD void reg_gather_even(const View& w, int k, StageTmp& T) {
 template <int STATE, class C>
 MPC_HD void reg_update(const View& w, const Params& p, const C& c, int k, StageRegs& R, StageTmp& T) {
   double* st = STATE ? R.r : w.rec(k);
-  pair_stage(st, st, w.rec(k), w.hdr(), p, c, w.N, k, T.xt, T.xn, T.ua, T.ud, T.G);
+  double* sx = STATE == 1 ? R.r : w.rec(k);
+  pair_stage(st, st, sx, sx, w.rec(k), w.hdr(), p, c, w.N, k, T.xt, T.xn, T.ua, T.ud, T.G);
   if (STATE) {                     // the record's state slots are stale inside a block: publish what the neighbours need
     double d[4];
-    stage_d(st, w.rec(k), c, k < w.N, d);
+    stage_d(sx, w.rec(k), c, k < w.N, d);
     double* mb = reg_mb(w, k);
 #pragma unroll
     for (int r = 0; r < 4; ++r) mb[r] = d[r];
@@ -144,15 +143,16 @@ MPC_HD void reg_rhs(const View& w, const Params& p, const C& c, const OEView& oe
     }
   }
   double val[6], d[4], base[6];
-  const double* st = STATE ? R.r : w.rec(k);
-  stage_d(st, w.rec(k), c, k < N, d);              // functions of the state: nothing but G is carried over B_c
-  stage_base(st, w.rec(k), c, k < N, base);
+  const double* sx = STATE == 1 ? R.r : w.rec(k);
+  stage_d(sx, w.rec(k), c, k < N, d);              // functions of the state: nothing but G is carried over B_c
+  stage_base(sx, w.rec(k), c, k < N, base);
   pair_assemble(w.rec(k) + R_LIN, p, N, k, dp, d, T.G, rn, base, val);
   if (k & 1) {
     double di[OE_SYM];
     sym_load(oe.dinv + OE_SYM * (k >> 1), di);
-    symv6(di, val, R.t);
-    row_store(w.nx(k), R.t);                            // for the even neighbours' fixup and the next expand
+    double t[6];
+    symv6(di, val, t);
+    row_store(w.nx(k), t);                              // for the even neighbours' fixup and the next expand
   } else {
 #pragma unroll
     for (int j = 0; j < 6; ++j) T.b[j] = val[j];

@@ -47,8 +47,12 @@ MPC_HD Residuals compute_residuals(Exec& ex, const View& w, const Params& p, con
 // warps per problem, every stage record in the registers of its lane for a block of iterations (mpc_reg.h).  Separate
 // instantiations, so a kernel carries one form.
 enum { FORM_GENERAL = 0, FORM_SHORT = 1, FORM_PAIR = 2, FORM_REG = 3 };
+template <class Exec>
+MPC_HD void solve_problem_reg(Exec& ex, const View& w, const Params& p, const Settings& s, const ProblemIO& io);   // mpc_drv.h
+
 template <int FORM, class Exec>
 MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settings& s, const ProblemIO& io) {
+  if constexpr (FORM == FORM_REG) { solve_problem_reg(ex, w, p, s, io); return; }
   const int N = w.N;
   const int NS = N + 1;
   int n_rho = 0, n_fac = 0, n_solve = 0, n_pol = 0;
@@ -231,25 +235,6 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
       need_factor = false;
       need_rhs = true;
     }
-    if constexpr (FORM == FORM_REG) {
-      // a block of iterations up to the next event (termination check, rho adaptation, iteration limit) with the stage
-      // records in registers; the first right-hand side after a (re)factorisation comes from the general parity passes
-      if (need_rhs) {
-        ex.tag(6);
-#pragma unroll 1
-        for (int par = 1; par >= 0; --par) ex.stages_par(NS, par, [&](int k) { admm_rhs_stage_oe(w, p, ic, oe, k); });
-        need_rhs = false;
-      }
-      int nb = s.max_iter - it;
-      if (s.check_termination > 0) { const int n = s.check_termination - it % s.check_termination; if (n < nb) nb = n; }
-      if (s.adaptive_rho && s.adaptive_rho_interval > 0) { const int n = s.adaptive_rho_interval - it % s.adaptive_rho_interval; if (n < nb) nb = n; }
-      if (nb < 1) nb = 1;
-      ex.tag(2);
-      ex.admm_block(w, p, ic, oe, nb);
-      it += nb; n_solve += nb;
-      after_update();
-      continue;
-    }
     ex.tag(6);
     if constexpr (FORM == FORM_SHORT) {
       ex.stages(NS, [&](int k) { admm_rhs_stage_short(w, p, ic, oe, k); });
@@ -297,3 +282,5 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
 }
 
 }  // namespace mpc
+
+#include "mpc_drv.h"
