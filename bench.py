@@ -215,7 +215,7 @@ def run_config2(torch, dev, stream, flush, local_rank, peak_tf, reps=30):
     out = {"workload": "4,096 independent tracking QPs, horizon 20, default limits (BASELINE.json configs[1]), seed 2; one launch, "
                        "256 MB written between launches to flush L2", "batch": B, "horizon": N}
     for name, early in (("early_polish", True), ("osqp_literal", False)):
-        ctl = MPCController(product_params(N, 0.15), SolverSettings(eps_abs=EPS, eps_rel=EPS, polish_passes=POLISH_PASSES, polish_retry=POLISH_RETRY,
+        ctl = MPCController(product_params(N, 0.15), SolverSettings(eps_abs=EPS, eps_rel=EPS, polish_passes=POLISH_PASSES, polish_retry=POLISH_RETRY, keep_iterate=False,
                                                                       early_polish=early), device=local_rank, max_batch=B)
         for _ in range(3):
             ctl.solve_batch(d[0], d[1], u_prev=d[2])
@@ -275,7 +275,7 @@ def run_config5(torch, dist, dev, stream, rank, world, local_rank):
     from rrt_mpc_b200.synthetic import make_batch
     start, count = shard_range(rank, world, SWEEP_BATCH)
     x0, ref, up = make_batch(SWEEP_BATCH, HORIZON, 5, start=start, count=count)
-    ctl = MPCController(product_params(), SolverSettings(eps_abs=EPS, eps_rel=EPS, polish_passes=POLISH_PASSES, polish_retry=POLISH_RETRY,
+    ctl = MPCController(product_params(), SolverSettings(eps_abs=EPS, eps_rel=EPS, polish_passes=POLISH_PASSES, polish_retry=POLISH_RETRY, keep_iterate=False,
                                                          early_polish=bool(EARLY_POLISH)), device=local_rank, max_batch=count)
     d = [torch.as_tensor(a).to(dev) for a in (x0, ref, up)]
     ctl.solve_batch(d[0][:BATCH], d[1][:BATCH], u_prev=d[2][:BATCH])
@@ -332,7 +332,7 @@ def main():
     N, B = HORIZON, args.batch
     warmup = max(3, args.warmup)
     params = product_params()
-    settings = SolverSettings(eps_abs=EPS, eps_rel=EPS, polish_passes=POLISH_PASSES, polish_retry=POLISH_RETRY, early_polish=bool(EARLY_POLISH))
+    settings = SolverSettings(eps_abs=EPS, eps_rel=EPS, polish_passes=POLISH_PASSES, polish_retry=POLISH_RETRY, keep_iterate=False, early_polish=bool(EARLY_POLISH))
     start, count = rank * B, B                      # weak scaling: every rank its own B problems of the seeded global batch
     x0, ref, up = make_batch(B * world, N, SEED, start=start, count=count)
     ctl = MPCController(params, settings, device=local_rank, max_batch=B)
@@ -376,7 +376,7 @@ def main():
     flops = flops_of_batch(N, iters, info[:, 1], info[:, 3])
 
     # ---- same batch, OSQP-literal termination (polish only after the ADMM residual test; no early polish) -----------
-    lit = SolverSettings(eps_abs=EPS, eps_rel=EPS, polish_passes=POLISH_PASSES, polish_retry=POLISH_RETRY, early_polish=False)
+    lit = SolverSettings(eps_abs=EPS, eps_rel=EPS, polish_passes=POLISH_PASSES, polish_retry=POLISH_RETRY, keep_iterate=False, early_polish=False)
     ctl.solve_batch(d_x0, d_ref, u_prev=d_up, settings=lit)
     sync()
     lit_ms = []
@@ -490,7 +490,7 @@ def main():
                    "polish_passes": POLISH_PASSES, "polish_retry": POLISH_RETRY, "early_polish": EARLY_POLISH, "parallelism": f"{world} x independent shards, no data-path collective",
                    "termination": "value: early certified polish (finishes as soon as a polish ends on a KKT point of a settled active set); "
                                   "value_literal: the same kernel with OSQP's own termination (residual test at eps 1e-6, then polish)",
-                   "l2": "working set per step (inputs 112 MB + outputs 161 MB + 803 MB warm-start state) exceeds the 126 MB L2; "
+                   "l2": "working set per step (inputs 112 MB + outputs 161 MB) exceeds the 126 MB L2 (stateless solves: keep_iterate=False, no per-problem warm-start state is written); "
                          "a 256 MB write flushes L2 between timed steps"},
         "solve_stats": {"solved_frac": sum(m["solved"] for m in allm) / (B * world), "iters_mean": float(np.mean([m["iters_mean"] for m in allm])),
                         "iters_max": max(m["iters_max"] for m in allm), "polished_frac": sum(m["polished"] for m in allm) / (B * world),

@@ -84,7 +84,10 @@ typedef struct cudampc_settings {
   int32_t adaptive_rho_interval; /* fixed iteration interval (upstream 0.6.x uses a wall-clock heuristic) */
   int32_t polish_passes;         /* 0 = no polish, 1 = OSQP's polish, >1 = re-identify the active set up to n times */
   int32_t polish_refine_iter;
-  int32_t warm_start;            /* 1: start from the iterate this handle stored for the same slot in the last call */
+  int32_t warm_start;            /* 1: start from the iterate this handle stored for the same slot in the last call;
+                                    0: cold start, the final iterate is stored for a later warm start; -1: stateless - cold
+                                    start and nothing is stored per problem (the solver's back-ups of the iterate then stay
+                                    in a few L2-resident slots, one per resident problem, instead of 12 KB of HBM per problem) */
   int32_t polish_retry;          /* if OSQP's polish is rejected (active set not identified): resume ADMM at a 10x tighter
                                     internal tolerance and polish again, up to this many times (0 = OSQP behaviour) */
   int32_t early_polish;          /* 1: also try the polish at termination checks whose guessed active set repeated; a polish that

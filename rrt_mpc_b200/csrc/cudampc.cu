@@ -164,7 +164,7 @@ __global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {
 struct cudampc_handle {
   int device, max_batch, N;
   Params p;
-  double *warm, *scratch, *work;
+  double *warm, *scratch, *work, *fsave;   // fsave: the ADMM factor of every resident group while a polish uses its place
   int* counter;
   // staging for the host-pointer entry point
   double *h_in, *h_out, *d_in, *d_out;
@@ -306,7 +306,7 @@ static int convert_settings(const cudampc_settings* in, Settings* s, cudampc_han
   // fixed fallback is a multiple of check_termination.  Map 0 to 2 * check_termination (= this library's default of 50).
   s->adaptive_rho_interval = in->adaptive_rho_interval > 0 ? in->adaptive_rho_interval : 2 * (in->check_termination > 0 ? in->check_termination : 25);
   s->polish_passes = in->polish_passes;
-  s->polish_refine_iter = in->polish_refine_iter; s->warm_start = in->warm_start;
+  s->polish_refine_iter = in->polish_refine_iter; s->warm_start = in->warm_start > 0 ? 1 : 0;   /* < 0: stateless, see solve_batch */
   s->polish_retry = in->polish_retry < 0 ? 0 : in->polish_retry;
   s->early_polish = in->early_polish; s->early_polish_start = in->early_polish_start;
   return CUDAMPC_OK;
@@ -393,12 +393,17 @@ int cudampc_create(const cudampc_params* params, int max_batch, int device, cuda
     e = solve_set_smem(h->variant, h->grp_smem);
     if (e != cudaSuccess) { delete h; return fail(nullptr, CUDAMPC_ERR_CUDA, "CUDA failure: %s", cudaGetErrorString(e)); }
   }
-  const size_t ws = (size_t)warm_size(p.N) * max_batch * sizeof(double);
+  // warm / scratch: one slot per problem of the largest batch, then one per resident group (stateless solves)
+  const size_t ws = (size_t)warm_size(p.N) * ((size_t)max_batch + (size_t)h->sms * h->grp_P) * sizeof(double);
   const size_t wk = (size_t)(16 + 4 * (p.N + 1) + 2 * p.N) * max_batch * sizeof(double);
   h->in_doubles = (size_t)max_batch * (4 + 4 * (p.N + 1) + 2);
   h->out_doubles = (size_t)max_batch * (2 + 4 * (p.N + 1) + 2 * p.N + 2 + 4);   // + pri, dua, (status, iters, info[4] as int32 in 3 doubles.. rounded to 4)
   e = cudaMalloc(&h->warm, ws);
   if (e == cudaSuccess) e = cudaMalloc(&h->scratch, ws);
+  {
+    int slots = h->sms * h->grp_P; if (h->sms * h->roll_per_sm > slots) slots = h->sms * h->roll_per_sm;
+    if (e == cudaSuccess) e = cudaMalloc(&h->fsave, (size_t)slots * oe_doubles(p.N) * sizeof(double));
+  }
   if (e == cudaSuccess) e = cudaMalloc(&h->work, wk);
   if (e == cudaSuccess) e = cudaMalloc(&h->counter, sizeof(int));
 #ifdef MPC_TIMING
@@ -418,7 +423,7 @@ int cudampc_create(const cudampc_params* params, int max_batch, int device, cuda
 int cudampc_destroy(cudampc_handle* h) {
   if (!h) return CUDAMPC_OK;
   DeviceGuard guard_(h->device);
-  cudaFree(h->warm); cudaFree(h->scratch); cudaFree(h->work); cudaFree(h->counter); cudaFree(h->tags);
+  cudaFree(h->warm); cudaFree(h->scratch); cudaFree(h->fsave); cudaFree(h->work); cudaFree(h->counter); cudaFree(h->tags);
   cudaFree(h->d_in); cudaFree(h->d_out);
   if (h->h_in) cudaFreeHost(h->h_in);
   if (h->h_out) cudaFreeHost(h->h_out);
@@ -507,7 +512,9 @@ int cudampc_solve_batch(cudampc_handle* h, int batch, const double* x0_dev, cons
   cudaStream_t st = (cudaStream_t)stream;
   CU(h, cudaMemsetAsync(h->counter, 0, sizeof(int), st));
   BatchArgs a;
-  a.x0 = x0_dev; a.ref = ref_dev; a.u_prev = u_prev_dev; a.warm = h->warm; a.scratch = h->scratch;
+  a.x0 = x0_dev; a.ref = ref_dev; a.u_prev = u_prev_dev; a.warm = h->warm; a.scratch = h->scratch; a.fsave = getenv("CUDAMPC_NO_FSAVE") ? nullptr : h->fsave;
+  a.group_state = settings && settings->warm_start < 0 ? 1 : 0;
+  a.group_slot0 = h->max_batch;
   a.u0 = u0_dev; a.Xp = Xp_dev; a.Up = Up_dev; a.status = status_dev; a.iters = iters_dev;
   a.pri = pri_res_dev; a.dua = dua_res_dev; a.info = info_dev; a.counter = h->counter; a.batch = batch; a.tags = h->tags;
   int grid = (batch + h->grp_P - 1) / h->grp_P;
@@ -632,7 +639,7 @@ int cudampc_rollout_batch(cudampc_handle* h, int batch, const double* ref_global
   CU(h, cudaMemsetAsync(h->counter, 0, sizeof(int), st));
   RolloutArgs a;
   a.ref_global = ref_global_dev; a.ref_len = ref_len_dev; a.ref_stride = ref_stride; a.state0 = state0_dev; a.goal = goal_dev;
-  a.warm = h->warm; a.scratch = h->scratch; a.work = h->work;
+  a.warm = h->warm; a.scratch = h->scratch; a.fsave = getenv("CUDAMPC_NO_FSAVE") ? nullptr : h->fsave; a.work = h->work;
   a.states = states_dev; a.controls = controls_dev; a.n_steps = n_steps_dev; a.flags = flags_dev;
   a.step_status = step_status_dev; a.step_iters = step_iters_dev; a.counter = h->counter; a.batch = batch;
   {

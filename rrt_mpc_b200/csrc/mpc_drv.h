@@ -124,6 +124,7 @@ MPC_HD void drv_after(Exec& ex, const View& w, const Params& p, const Settings& 
         });
       }
       if (attempt && can_polish) {
+        if (io.fsave && !last && !(converged && d.retries <= 0)) ex.stages(oe_doubles(w.N), [&](int i) { oe_save_word(w, i, io.fsave); });
         // ---- polish (solve_problem: polish lambda) ----
         const Mode pm = polish_mode(s);
         const PolConst pc = pol_const(w, p, s);
@@ -175,7 +176,8 @@ MPC_HD void drv_after(Exec& ex, const View& w, const Params& p, const Settings& 
           ex.tag(13);
           ex.stages(NS, [&](int k) { load_stage(w, k, io.warm); });
           ex.single([&]() { for (int r = 0; r < 4; ++r) w.hdr()[H_YI + r] = io.warm[30 * NS + r]; });
-          d.need_factor = 1;
+          if (io.fsave) { ex.stages(oe_doubles(w.N), [&](int i) { oe_restore_word(w, i, io.fsave); }); d.need_rhs = 1; }
+          else d.need_factor = 1;
         }
       } else {
         d.finished = 1;

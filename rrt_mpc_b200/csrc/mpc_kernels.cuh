@@ -10,10 +10,12 @@ using namespace mpc;
 
 struct BatchArgs {
   const double* x0; const double* ref; const double* u_prev;
-  double* warm; double* scratch;
+  double* warm; double* scratch; double* fsave;     // fsave: oe_doubles(N) per resident group (grid x P), or null
   double* u0; double* Xp; double* Up; int* status; int* iters; double* pri; double* dua; int* info;
   int* counter;
   int batch;
+  int group_state;             // 1: stateless solve - the iterate back-ups (warm, scratch) use the resident group's slot, not the problem's
+  int group_slot0;             // first of the per-group slots (behind the per-problem ones)
   unsigned long long* tags;    // dev builds only (MPC_TIMING)
 };
 
@@ -39,8 +41,10 @@ __global__ void __launch_bounds__(MAXT, 1) mpc_solve_kernel(Params p, Settings s
     io.x0 = a.x0 + 4 * (size_t)b;
     io.ref = RefWin{a.ref + (size_t)4 * (N + 1) * b, 0, N + 1, 1.0};
     io.u_prev = a.u_prev ? a.u_prev + 2 * (size_t)b : nullptr;
-    io.warm = a.warm + (size_t)ws * b;
-    io.scratch = a.scratch + (size_t)ws * b;
+    const size_t slot = a.group_state ? (size_t)a.group_slot0 + (size_t)blockIdx.x * P + warp / WPP : (size_t)b;
+    io.warm = a.warm + (size_t)ws * slot;
+    io.scratch = a.scratch + (size_t)ws * slot;
+    io.fsave = a.fsave ? a.fsave + (size_t)oe_doubles(N) * ((size_t)blockIdx.x * P + warp / WPP) : nullptr;
     io.u0 = a.u0 + 2 * (size_t)b;
     io.Xp = a.Xp + (size_t)4 * (N + 1) * b;
     io.Up = a.Up + (size_t)2 * N * b;
@@ -56,14 +60,16 @@ __global__ void __launch_bounds__(MAXT, 1) mpc_solve_kernel(Params p, Settings s
 // K_solve, register form (mpc_reg.h, mpc_drv.h): two warps per problem; the iteration blocks are inlined HERE, at the top
 // level of the kernel, and everything else of the driver runs in three real calls that keep their state in shared memory.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ ProblemIO batch_io(const BatchArgs& a, int b, int N) {
+__device__ __forceinline__ ProblemIO batch_io(const BatchArgs& a, int b, int N, int group) {
   const int ws = warm_size(N);
   ProblemIO io;
   io.x0 = a.x0 + 4 * (size_t)b;
   io.ref = RefWin{a.ref + (size_t)4 * (N + 1) * b, 0, N + 1, 1.0};
   io.u_prev = a.u_prev ? a.u_prev + 2 * (size_t)b : nullptr;
-  io.warm = a.warm + (size_t)ws * b;
-  io.scratch = a.scratch + (size_t)ws * b;
+  const size_t slot = a.group_state ? (size_t)a.group_slot0 + (size_t)group : (size_t)b;
+  io.warm = a.warm + (size_t)ws * slot;
+  io.scratch = a.scratch + (size_t)ws * slot;
+  io.fsave = a.fsave ? a.fsave + (size_t)oe_doubles(N) * group : nullptr;
   io.u0 = a.u0 + 2 * (size_t)b;
   io.Xp = a.Xp + (size_t)4 * (N + 1) * b;
   io.Up = a.Up + (size_t)2 * N * b;
@@ -72,7 +78,7 @@ __device__ __forceinline__ ProblemIO batch_io(const BatchArgs& a, int b, int N) 
   io.info = a.info ? a.info + 4 * (size_t)b : nullptr;
   return io;
 }
-struct RegCtx { const Params* p; const Settings* s; const BatchArgs* a; double* base; GroupShared* sh; int N, fpad, xpad, lane, warp; };
+struct RegCtx { const Params* p; const Settings* s; const BatchArgs* a; double* base; GroupShared* sh; int N, fpad, xpad, lane, warp, group; };
 __device__ __forceinline__ GroupExec<2> reg_exec(const RegCtx& c) {
   GroupExec<2> ex{c.lane, c.warp, c.sh};
 #ifdef MPC_TIMING
@@ -83,7 +89,7 @@ __device__ __forceinline__ GroupExec<2> reg_exec(const RegCtx& c) {
 __device__ __forceinline__ void reg_drv_begin(RegCtx c, int b) {
   const View w{c.base, c.N, c.fpad, c.xpad};
   GroupExec<2> ex = reg_exec(c);
-  const ProblemIO io = batch_io(*c.a, b, c.N);
+  const ProblemIO io = batch_io(*c.a, b, c.N, c.group);
   Drv d;
   drv_begin(ex, w, *c.p, *c.s, io, d);
   drv_prepare(ex, w, *c.p, *c.s, d);
@@ -93,7 +99,7 @@ __device__ __forceinline__ void reg_drv_begin(RegCtx c, int b) {
 __device__ __forceinline__ void reg_drv_after(RegCtx c, int b) {
   const View w{c.base, c.N, c.fpad, c.xpad};
   GroupExec<2> ex = reg_exec(c);
-  const ProblemIO io = batch_io(*c.a, b, c.N);
+  const ProblemIO io = batch_io(*c.a, b, c.N, c.group);
   Drv d = c.sh->drv;
   ex.group_sync();                          // every lane has its copy before lane 0 writes the new one
   drv_after(ex, w, *c.p, *c.s, io, d);
@@ -104,7 +110,7 @@ __device__ __forceinline__ void reg_drv_after(RegCtx c, int b) {
 __device__ __forceinline__ void reg_drv_finish(RegCtx c, int b) {
   const View w{c.base, c.N, c.fpad, c.xpad};
   GroupExec<2> ex = reg_exec(c);
-  const ProblemIO io = batch_io(*c.a, b, c.N);
+  const ProblemIO io = batch_io(*c.a, b, c.N, c.group);
   const Drv d = c.sh->drv;
   drv_finish(ex, w, io, d);
   ex.group_sync();
@@ -128,7 +134,7 @@ __global__ void __launch_bounds__(MAXT, 1) mpc_solve_reg_kernel(const __grid_con
   for (int b = ex.fetch(a.counter); b < a.batch; b = ex.fetch(a.counter)) {
     // The pieces of the driver are inlined; none of their values is alive across a block (Drv lives in shared memory
     // between them).
-    const RegCtx c{&p, &s, &a, base, sh, N, fpad, xpad, lane, warp};
+    const RegCtx c{&p, &s, &a, base, sh, N, fpad, xpad, lane, warp, (int)blockIdx.x * P + warp / 2};
     reg_drv_begin(c, b);
     while (!*(volatile int*)&sh->drv.finished) {
       const int nb = *(volatile int*)&sh->drv.nb;
@@ -154,7 +160,7 @@ __device__ __forceinline__ void f_discrete_vals(double dt, double L, const doubl
 struct RolloutArgs {
   const double* ref_global; const int* ref_len; int ref_stride;
   const double* state0; const double* goal;
-  double* warm; double* scratch; double* work;   // work: per vehicle 16 doubles (state, u_prev, u0 out) + Xp/Up scratch
+  double* warm; double* scratch; double* fsave; double* work;   // fsave: oe_doubles(N) per CTA, or null; work: per vehicle 16 doubles (state, u_prev, u0 out) + Xp/Up scratch
   double* states; double* controls; int* n_steps; int* flags; int* step_status; int* step_iters;
   int* counter; int batch;
 };
@@ -197,6 +203,7 @@ __device__ __forceinline__ void rollout_vehicle(Exec& ex, const View& w, const P
     io.x0 = wkb; io.u_prev = wkb + 4;
     io.ref = RefWin{refg, path_idx, len, 1.0};
     io.warm = a.warm + (size_t)ws * b; io.scratch = a.scratch + (size_t)ws * b;
+    io.fsave = a.fsave ? a.fsave + (size_t)oe_doubles(N) * blockIdx.x : nullptr;
     io.u0 = wkb + 6; io.Xp = wkb + 16; io.Up = wkb + 16 + 4 * (N + 1);
     io.status = st_out; io.iters = it_out; io.pri_res = nullptr; io.dua_res = nullptr; io.info = nullptr;
     Settings ss = s;

@@ -51,6 +51,15 @@ MPC_HD OEView oe_view(const View& w) {
   return o;
 }
 
+// doubles of the factor (dinv, sinv, gt, pad, gb) behind band_offset(N): what a polish overwrites and a resume needs back
+MPC_HD int oe_doubles(int N) { return OE_SYM * (oe_nodd(N) + oe_neven(N)) + OE_G * (oe_neven(N) - 1) + 2; }
+// element i of the factor area <-> a per-group slot in global memory (lanes stride over i: coalesced)
+MPC_HD void oe_save_word(const View& w, int i, double* g) { g[i] = (w.base + band_offset(w.N))[i]; }
+MPC_HD void oe_restore_word(const View& w, int i, const double* g) {
+  (w.base + band_offset(w.N))[i] = g[i];
+  if (i < BXS) w.nx_zero()[i] = 0.0;                      // the row of zeros the bottom half reads (the polish used the rows)
+}
+
 // ------------------------------------------------------------------------------------------------
 // 6x6 helpers
 // ------------------------------------------------------------------------------------------------

@@ -15,6 +15,7 @@ struct ProblemIO {
   const double* u_prev;  // [2]
   double* warm;          // HBM slot, warm_size(N) doubles (ADMM iterate; also polish back-up)
   double* scratch;       // HBM slot, warm_size(N) doubles (polished-solution back-up between passes)
+  double* fsave;         // HBM slot of the resident group, oe_doubles(N) doubles: the ADMM factor while a polish uses its place (or null)
   double* u0;            // [2]
   double* Xp;            // [4][N+1] state-major (visualization.py:244-245)
   double* Up;            // [2][N]
@@ -166,7 +167,8 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
     ex.tag(13);
     ex.stages(NS, [&](int k) { load_stage(w, k, io.warm); });
     ex.single([&]() { for (int r = 0; r < 4; ++r) w.hdr()[H_YI + r] = io.warm[30 * NS + r]; });
-    need_factor = true;
+    if (io.fsave) { ex.stages(oe_doubles(N), [&](int i) { oe_restore_word(w, i, io.fsave); }); need_rhs = true; }   // rho is unchanged: the saved factor is valid
+    else need_factor = true;
   };
 
   // NOTE: every multi-statement lambda above has exactly ONE call site below, so that it is inlined and the solver
@@ -198,6 +200,8 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
           ex.tag(8);
           if (io.warm) save_iterate();
           if (attempt && can_polish) {
+            // the polish factorises in the place of the ADMM factor: keep a copy unless this is certainly the last polish
+            if (io.fsave && !last && !(converged && retries <= 0)) ex.stages(oe_doubles(N), [&](int i) { oe_save_word(w, i, io.fsave); });
             const bool clean = polish(res.pri, res.dua);
             if (clean) { status = STATUS_SOLVED; finished = true; }
             else if (last || (converged && retries <= 0)) {                      // keep what the polish gave (OSQP behaviour)

@@ -63,6 +63,7 @@ class SolverSettings:
     delta: float = 1e-6
     polish_refine_iter: int = 3
     warm_start: bool = False      # upstream's warm_start=True is a no-op (a new Problem per call)
+    keep_iterate: bool = True     # False (with warm_start False): stateless solve, nothing is stored per problem for a later warm start
     polish_retry: int = 0         # rejected polish -> resume ADMM at 10x tighter internal eps, polish again (0 = OSQP)
     early_polish: bool = False    # try the polish as soon as the guessed active set repeats; finish if it certifies a KKT point
     early_polish_start: int = 50
@@ -76,7 +77,8 @@ class SolverSettings:
         s.adaptive_rho, s.rho, s.alpha, s.sigma = int(self.adaptive_rho), self.rho, self.alpha, self.sigma
         s.check_termination, s.adaptive_rho_interval = int(self.check_termination), int(self.adaptive_rho_interval)
         s.adaptive_rho_tolerance, s.delta = self.adaptive_rho_tolerance, self.delta
-        s.polish_refine_iter, s.warm_start = int(self.polish_refine_iter), int(self.warm_start)
+        s.polish_refine_iter = int(self.polish_refine_iter)
+        s.warm_start = 1 if self.warm_start else (0 if self.keep_iterate else -1)
         s.polish_retry = int(self.polish_retry)
         s.early_polish, s.early_polish_start = int(self.early_polish), int(self.early_polish_start)
         return s

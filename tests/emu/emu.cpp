@@ -90,6 +90,8 @@ static void unpack(const double* par, const double* set, int N, Params& p, Setti
   s.warm_start = (int)set[i++]; s.polish_retry = (int)set[i++]; s.early_polish = (int)set[i++]; s.early_polish_start = (int)set[i++];
 }
 
+static int g_fsave = 1;       // keep the ADMM factor in a side buffer over a polish (0: refactorise on resume)
+void emu_set_fsave(int f) { g_fsave = f; }
 static int g_form = -1;      // -1: what the library picks (short form for N+1 <= 32, pair form for N+1 <= 64), else FORM_* of mpc_solve.h
 void emu_set_form(int f) { g_form = f & 3; g_reg_state = (f & 4) ? 0 : 1; if (f < 0) { g_form = -1; g_reg_state = 1; } }
 
@@ -97,7 +99,7 @@ int emu_solve_batch(const double* par, const double* set, int N, int B, int reve
                     const double* x0, const double* ref, const double* u_prev, double* warm,
                     double* u0, double* Xp, double* Up, int* status, int* iters, double* pri, double* dua, int* info) {
   Params p; Settings s; unpack(par, set, N, p, s);
-  std::vector<double> ws(footprint(N)), scratch(warm_size(N)), warm_local(warm_size(N));
+  std::vector<double> ws(footprint(N)), scratch(warm_size(N)), warm_local(warm_size(N)), fsave(oe_doubles(N));
   for (int b = 0; b < B; ++b) {
     std::fill(ws.begin(), ws.end(), 0.0);
     View w{ws.data(), N, 4, 2};   // arbitrary non-zero (even: 16-byte aligned) pads: the layout must work with any
@@ -105,6 +107,7 @@ int emu_solve_batch(const double* par, const double* set, int N, int B, int reve
     io.x0 = x0 + 4 * b; io.ref = RefWin{ref + (size_t)4 * (N + 1) * b, 0, N + 1, 1.0}; io.u_prev = u_prev ? u_prev + 2 * b : nullptr;
     io.warm = warm ? warm + (size_t)warm_size(N) * b : warm_local.data();
     io.scratch = scratch.data();
+    io.fsave = g_fsave ? fsave.data() : nullptr;
     io.u0 = u0 + 2 * b; io.Xp = Xp + (size_t)4 * (N + 1) * b; io.Up = Up + (size_t)2 * N * b;
     io.status = status + b; io.iters = iters + b; io.pri_res = pri + b; io.dua_res = dua + b; io.info = info + 4 * b;
     Settings sb = s;

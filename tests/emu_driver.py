@@ -54,6 +54,11 @@ def set_form(form):
     lib().emu_set_form(int(form))
 
 
+def set_fsave(on):
+    """1: the ADMM factor is kept in a side buffer while a polish uses its place; 0: it is recomputed when ADMM resumes."""
+    lib().emu_set_fsave(int(on))
+
+
 def warm_size(N):
     return lib().emu_warm_size(N)
 

@@ -220,3 +220,26 @@ def test_pair_and_general_form_of_the_phases_agree(N, du, form):
     assert (a["status"] == 1).all()
     for k in ("u0", "Xp", "Up", "iters", "status", "info"):
         assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], ar[k]), k
+
+
+def test_saved_factor_equals_refactorisation_on_resume():
+    """A polish factorises in the place of the ADMM factor.  When ADMM resumes after a rejected / unsettled polish the factor
+    comes back from a side buffer (rho is unchanged) instead of being recomputed: the same numbers, so the solves agree to the
+    last bit; only the factorisation count drops."""
+    g = load_golden("optima.npz")
+    for name, N, du, form in (("n20", 20, 0.15, -1), ("n50", 50, 0.02, 0), ("n50", 50, 0.02, 3)):
+        p = oracle_params(N, du)
+        nb = 16
+        kw = dict(polish_passes=5, polish_retry=2, early_polish=1, **TIGHT)
+        try:
+            E.set_form(form)
+            E.set_fsave(1)
+            a = E.solve(p, g[f"{name}_x0"][:nb], g[f"{name}_ref"][:nb], g[f"{name}_up"][:nb], **kw)
+            E.set_fsave(0)
+            b = E.solve(p, g[f"{name}_x0"][:nb], g[f"{name}_ref"][:nb], g[f"{name}_up"][:nb], **kw)
+        finally:
+            E.set_fsave(1)
+            E.set_form(-1)
+        for k in ("u0", "Xp", "Up", "iters", "status"):
+            assert np.array_equal(a[k], b[k]), k
+        assert a["info"][:, 1].sum() < b["info"][:, 1].sum()          # fewer factorisations

@@ -174,6 +174,23 @@ def test_warm_start_same_optimum_fewer_iterations():
     assert cold.iters.sum() > 0
 
 
+def test_stateless_solve_is_the_same_solve_and_leaves_the_slots_alone():
+    """keep_iterate=False (C ABI: warm_start = -1): the iterate back-ups live in per-resident-problem slots instead of the
+    problem's own warm-start slot.  Same arithmetic, so the results are identical; a later warm start finds no stored iterate
+    and starts cold."""
+    from rrt_mpc_b200 import SolverSettings
+    g = load_golden("optima.npz")
+    x0, ref, up = g["n20_x0"], g["n20_ref"], g["n20_up"]
+    kw = dict(polish_passes=5, polish_retry=2, early_polish=True, **TIGHT)
+    a = controller(20).solve_batch(x0, ref, u_prev=up, settings=SolverSettings(**kw))
+    ctl = controller(20)
+    b = ctl.solve_batch(x0, ref, u_prev=up, settings=SolverSettings(keep_iterate=False, **kw))
+    for k in ("u0", "Xp", "Up", "iters", "status"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    hot = ctl.solve_batch(x0, ref, u_prev=up, settings=SolverSettings(warm_start=True, **kw))     # nothing was stored: cold
+    assert np.array_equal(hot.iters, a.iters)
+
+
 def test_invalid_arguments_fail_loudly():
     ctl = controller(20)
     with pytest.raises(ValueError):
