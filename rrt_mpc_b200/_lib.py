@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcudampc.so")
+LIB_PATH = os.environ.get("CUDAMPC_LIB") or os.path.join(_HERE, "libcudampc.so")      # CUDAMPC_LIB: dev builds (timing, poison)
 
 
 class Params(C.Structure):

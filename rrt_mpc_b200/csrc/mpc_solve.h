@@ -265,6 +265,11 @@ MPC_HD void solve_problem(Exec& ex, const View& w, const Params& p, const Settin
 #pragma unroll 1
       for (int par = 1; par >= 0; --par) ex.stages_par(NS, par, [&](int k) { admm_update_stage_oe(w, p, ic, oe, k); });
     }
+#ifdef MPC_POISON      // dev builds (tools/poison_check.py): after the update every right-hand side / solution row is dead until the next
+                       // right-hand side pass rewrites it - a phase that read one earlier (a missing barrier between the warps of a
+                       // group, a wrong row index) would now read a NaN and the solve could not reach its optimum
+    ex.stages(NS, [&](int k) { double* r_ = w.nx(k); const double nan_ = (w.N - w.N) / (double)(w.N - w.N); for (int j = 0; j < BXS; ++j) r_[j] = nan_; });
+#endif
     after_update();
   }
   ex.tag(7);

@@ -60,6 +60,41 @@ __device__ __forceinline__ void fwd_shfl6(int lane, const View& w, const OEView&
   if (lane < 6) mrow[r] = ymid + yo;
   __syncwarp();
 }
+// V3: as V1 but inside the 12-lane divergent region of the shipped sweeps (shuffles over the 12-lane mask, no barrier at all)
+__device__ __forceinline__ void fwd_shfl6_region(int lane, const View& w, const OEView& oe) {
+  if (lane < 12) {
+    const bool bottom = lane >= 6; const int r = bottom ? lane - 6 : lane; const int base = bottom ? 6 : 0;
+    const OEHalf h = oe_half(w, oe, bottom);
+    const int cnt = h.cnt, cmax = oe.jm > oe.nb ? oe.jm : oe.nb;
+    const int xs = h.xstep * 8;
+    const unsigned xlast = smem_u32(h.xlast) + 8 * r;
+    unsigned xrow = smem_u32(h.x0) + xs, gp = smem_u32(h.g0) + 48 * r;
+    double a[6], gA[6], gB[6], nbA, nbB, y;
+    lds_row(smem_u32(h.x0), a);
+    double ymid = lds_f64(xlast);
+    lds_row(gp, gA); nbA = lds_f64(cnt == 1 ? xlast : xrow + 8 * r);
+    for (int i = 1; i <= cmax; i += 2) {
+      lds_row(gp + 288, gB); nbB = lds_f64(i + 1 == cnt ? xlast : xrow + xs + 8 * r);
+      y = oe_row_dot(gA, nbA, a);
+      ymid = (i == cnt) ? y : ymid;
+      sts_f64_if(i < cnt, xrow + 8 * r, y);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) a[c] = __shfl_sync(0xfffu, y, base + c);
+      if (i + 1 > cmax) break;
+      lds_row(gp + 576, gA); nbA = lds_f64(i + 2 == cnt ? xlast : xrow + 2 * xs + 8 * r);
+      y = oe_row_dot(gB, nbB, a);
+      ymid = (i + 1 == cnt) ? y : ymid;
+      sts_f64_if(i + 1 < cnt, xrow + xs + 8 * r, y);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) a[c] = __shfl_sync(0xfffu, y, base + c);
+      gp += 576; xrow += 2 * xs;
+    }
+    const double yo = __shfl_sync(0xfffu, ymid, bottom ? lane - 6 : lane + 6);
+    double* mrow = w.nx(2 * oe.jm);
+    if (lane < 6) mrow[r] = ymid + yo;
+  }
+  __syncwarp();
+}
 // V2: 2 lanes per half, 3 rows each (18 fmas), three values exchanged by shuffle
 __device__ __forceinline__ void fwd_shfl2(int lane, const View& w, const OEView& oe) {
   const bool act = lane < 4; const bool bottom = (lane >> 1) & 1; const int q = lane & 1;     // rows 3q .. 3q+2
@@ -98,7 +133,7 @@ __global__ void bench_var(int N, int F, int reps, long long* cyc, double* sink) 
   long long tf = 0;
   for (int r = 0; r < reps; ++r) {
     long long t0 = clock64();
-    if (VAR == 0) oe_forward_lanes(lane, w, oe); else if (VAR == 1) fwd_shfl6(lane, w, oe); else fwd_shfl2(lane, w, oe);
+    if (VAR == 0) oe_forward_lanes(lane, w, oe); else if (VAR == 1) fwd_shfl6(lane, w, oe); else if (VAR == 3) fwd_shfl6_region(lane, w, oe); else fwd_shfl2(lane, w, oe);
     __syncwarp();
     tf += clock64() - t0;
     for (int k = lane; k <= N; k += 32) { double* x = w.nx(k); for (int t = 0; t < 6; ++t) x[t] = 1.0 + 0.01 * ((k + t + r) % 9); }
@@ -167,15 +202,17 @@ int main(int argc, char** argv) {
   CK(cudaFuncSetAttribute(bench_var<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CK(cudaFuncSetAttribute(bench_var<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CK(cudaFuncSetAttribute(bench_var<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  for (int var = 0; var < 3; ++var)
+  CK(cudaFuncSetAttribute(bench_var<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  for (int var = 0; var < 4; ++var)
     for (int wi = 0; wi < 5; ++wi) {
       int W = ws[wi]; if (W > maxw) continue;
       if (var == 0) bench_var<0><<<148, 32 * W, W * F * 8>>>(N, F, 50, cyc, sink);
       else if (var == 1) bench_var<1><<<148, 32 * W, W * F * 8>>>(N, F, 50, cyc, sink);
-      else bench_var<2><<<148, 32 * W, W * F * 8>>>(N, F, 50, cyc, sink);
+      else if (var == 2) bench_var<2><<<148, 32 * W, W * F * 8>>>(N, F, 50, cyc, sink);
+      else bench_var<3><<<148, 32 * W, W * F * 8>>>(N, F, 50, cyc, sink);
       CK(cudaDeviceSynchronize());
       long long h[1]; CK(cudaMemcpy(h, cyc, 8, cudaMemcpyDeviceToHost));
-      printf("N=%d warps/SM=%d forward variant %d (0 smem exchange, 1 shuffle x6 lanes, 2 shuffle 2 lanes x 3 rows): %lld cycles (%.0f/step)\n", N, W, var, h[0], (double)h[0] / oe_mid(N));
+      printf("N=%d warps/SM=%d forward variant %d (0 shipped: smem exchange in a 12-lane region, 1 shuffle x6 lanes all lanes converged, 2 shuffle 2 lanes x 3 rows, 3 shuffle x6 lanes in the 12-lane region): %lld cycles (%.0f/step)\n", N, W, var, h[0], (double)h[0] / oe_mid(N));
     }
   return 0;
 }
