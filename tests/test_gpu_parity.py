@@ -191,6 +191,30 @@ def test_stateless_solve_is_the_same_solve_and_leaves_the_slots_alone():
     assert np.array_equal(hot.iters, a.iters)
 
 
+@pytest.mark.parametrize("form", ["reg", "pair", "general"])
+@pytest.mark.parametrize("name,N,du", [("n50", 50, 0.02), ("n20", 20, 0.15)])
+def test_forms_of_the_iteration_agree_on_the_device(form, name, N, du, monkeypatch):
+    """The library picks the form of the ADMM iteration from the horizon (short: a lane per stage; general: one parity of stages
+    at a time); the pair form and the two-warp register form (mpc_solve_reg_kernel: stage records in registers over a block of
+    iterations) are selected with CUDAMPC_FORM.  Every sum has the same operands and order in all of them, so status, iteration
+    counts and results are identical to the last bit."""
+    import dataclasses
+    from rrt_mpc_b200 import MPCConfig, MPCController, SolverSettings
+    g = load_golden("optima.npz")
+    par = MPCConfig(horizon=N).to_parameters(0.8)
+    par = dataclasses.replace(par, du_bounds=((-12.0, 12.0), (-du, du)))
+    x0, ref, up = g[f"{name}_x0"], g[f"{name}_ref"], g[f"{name}_up"]
+    st = SolverSettings(polish_passes=5, polish_retry=2, early_polish=True, **TIGHT)
+    monkeypatch.delenv("CUDAMPC_FORM", raising=False)
+    a = MPCController(par, st, max_batch=len(x0)).solve_batch(x0, ref, u_prev=up)
+    monkeypatch.setenv("CUDAMPC_FORM", form)
+    b = MPCController(par, st, max_batch=len(x0)).solve_batch(x0, ref, u_prev=up)
+    assert (a.status == 1).all()
+    for k in ("status", "iters", "u0", "Xp", "Up"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), (form, k)
+    assert np.abs(a.u0 - g[f"{name}_u0"]).max() < 1e-8
+
+
 def test_invalid_arguments_fail_loudly():
     ctl = controller(20)
     with pytest.raises(ValueError):
