@@ -245,7 +245,7 @@ def run_config4(torch, dev, local_rank, vehicles=8192, steps=500):
     starts = path[0] + rng.normal(size=(vehicles, 2)) * 0.5
     goals = np.full((vehicles, 2), 1e9)
     tr = TrajectoryTracker(MPCConfig(sim_steps=steps), None, device=local_rank,
-                           settings=SolverSettings(eps_abs=EPS, eps_rel=EPS, polish_passes=POLISH_PASSES, polish_retry=POLISH_RETRY, early_polish=False))
+                           settings=SolverSettings(eps_abs=EPS, eps_rel=EPS, polish_passes=POLISH_PASSES, polish_retry=2, early_polish=False))
     tr.track_batch(paths[:512], starts[:512], goals[:512], map_resolution=0.8, warm_start=True, sim_steps=50)      # warm-up
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -257,11 +257,26 @@ def run_config4(torch, dev, local_rank, vehicles=8192, steps=500):
     wall = time.perf_counter() - t
     n = int(res.n_steps.sum())
     ns = res.step_ns[res.step_status != 0].astype(np.float64)
+    # A vehicle's steps are sequential, so the launch ends with its slowest vehicle.  A few of the perturbed vehicles lose the
+    # path (spinning, |yaw| of several turns) and need 10-20x the iterations of the others at every step: report what the
+    # device sustains while all its slots are busy next to the wall-clock rate.
+    per_vehicle_s = res.step_ns.astype(np.float64).sum(axis=1) / 1e9
+    slots = min(vehicles, tr._controller(tr.mpc.to_parameters(0.8), key="rollout").rollout_resident())
+    busy_s = float(per_vehicle_s.sum())
+    speed = np.abs(res.states[:, :, 3])
     return {"workload": f"{vehicles} vehicles x {steps} closed-loop steps along perturbed copies of the default RRT* path (BASELINE.json configs[3]), "
                         "horizon 15, warm start, OSQP-literal termination + polish, references built on the device, one K_rollout launch",
             "vehicles": vehicles, "sim_steps": steps, "vehicle_steps": n, "value": n / wall, "unit": "vehicle-steps/s (= closed-loop MPC solves/s)",
             "wall_s": wall, "device_ms_incl_reference_build_and_d2h": float(e0.elapsed_time(e1)), "aborted": int(res.aborted.sum()),
             "relaxed": int(res.relaxed.sum()), "iters_mean_per_step": float(res.step_iters[res.step_status != 0].mean()),
+            "settings": "eps 1e-6, polish_passes 5, polish_retry 2 (the closed-loop tests' settings), warm start",
+            "resident_vehicles": int(slots),
+            "value_all_slots_busy": n / (busy_s / slots) if busy_s > 0 else None,
+            "slowest_vehicle_s": float(per_vehicle_s.max()), "median_vehicle_s": float(np.median(per_vehicle_s)),
+            "moving_steps_frac": float(np.nanmean(speed > 0.5)),
+            "note": "wall clock = slowest vehicle: the launch ends when the last sequential 500-step chain ends; value_all_slots_busy = steps / "
+                    "(sum of all step times / resident vehicles); vehicles reach the end of the 45-point path after ~100 steps and hold "
+                    "position for the rest (moving_steps_frac)",
             "step_latency_us": {"p50": float(np.percentile(ns, 50)) / 1e3, "p99": float(np.percentile(ns, 99)) / 1e3, "max": float(ns.max()) / 1e3,
                                 "mean": float(ns.mean()) / 1e3, "samples": int(ns.size),
                                 "note": "one closed-loop step of one vehicle (window gather, solve, f_discrete, path-index rule) while "

@@ -179,6 +179,7 @@ int cudampc_rollout_batch(cudampc_handle* h, int batch, const double* ref_global
  * number of kernel launches issued by this handle so far. */
 int cudampc_workspace_doubles(const cudampc_handle* h);
 int cudampc_problems_per_sm(const cudampc_handle* h);
+int cudampc_rollout_resident(const cudampc_handle* h);   /* vehicles K_rollout keeps in flight on the device (SMs x resident one-warp CTAs) */
 int64_t cudampc_launch_count(const cudampc_handle* h);
 
 /* Measured fp64 FMA throughput of the handle's device (TFLOP/s, ~50 ms of independent DFMA chains): the

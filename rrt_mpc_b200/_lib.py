@@ -37,7 +37,7 @@ SYMBOLS = (
     "cudampc_version", "cudampc_default_settings", "cudampc_default_rollout_cfg", "cudampc_create",
     "cudampc_destroy", "cudampc_last_error", "cudampc_set_params", "cudampc_linearize_batch", "cudampc_f_discrete_batch",
     "cudampc_solve_batch", "cudampc_solve_batch_host", "cudampc_build_reference_batch", "cudampc_rollout_batch", "cudampc_workspace_doubles",
-    "cudampc_problems_per_sm", "cudampc_launch_count", "cudampc_fp64_peak_tflops",
+    "cudampc_problems_per_sm", "cudampc_rollout_resident", "cudampc_launch_count", "cudampc_fp64_peak_tflops",
 )
 
 _lib = None
@@ -84,6 +84,8 @@ def load() -> C.CDLL:
     lib.cudampc_workspace_doubles.restype = C.c_int
     lib.cudampc_problems_per_sm.argtypes = [vp]
     lib.cudampc_problems_per_sm.restype = C.c_int
+    lib.cudampc_rollout_resident.argtypes = [vp]
+    lib.cudampc_rollout_resident.restype = C.c_int
     lib.cudampc_launch_count.argtypes = [vp]
     lib.cudampc_launch_count.restype = C.c_int64
     lib.cudampc_fp64_peak_tflops.argtypes = [vp]

@@ -466,6 +466,7 @@ double cudampc_fp64_peak_tflops(cudampc_handle* h) {
 
 int cudampc_workspace_doubles(const cudampc_handle* h) { return h ? footprint(h->N) : 0; }
 int cudampc_problems_per_sm(const cudampc_handle* h) { return h ? h->grp_P : 0; }
+int cudampc_rollout_resident(const cudampc_handle* h) { return h ? h->sms * h->roll_per_sm : 0; }
 int64_t cudampc_launch_count(const cudampc_handle* h) { return h ? h->launches : 0; }
 
 int cudampc_linearize_batch(cudampc_handle* h, int batch, const double* ref_dev, double* A_dev, double* B_dev,

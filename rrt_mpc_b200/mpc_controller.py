@@ -177,6 +177,11 @@ class MPCController:
         h = self._handle(1)
         return int(h.lib.cudampc_problems_per_sm(h.ptr))
 
+    def rollout_resident(self) -> int:
+        """Vehicles the closed-loop kernel keeps in flight on the device."""
+        h = self._handle(1)
+        return int(h.lib.cudampc_rollout_resident(h.ptr))
+
     def fp64_peak_tflops(self) -> float:
         h = self._handle(1)
         return float(h.lib.cudampc_fp64_peak_tflops(h.ptr))
