@@ -181,25 +181,27 @@ struct cudampc_handle {
 static char g_create_err[512] = "";
 
 // launchers of the kernel instantiations (mpc_kernels_tu.cu, one translation unit each)
-cudaError_t solve_set_smem_0(int), solve_set_smem_1(int), solve_set_smem_2(int), solve_set_smem_3(int), solve_set_smem_4(int);
+cudaError_t solve_set_smem_0(int), solve_set_smem_1(int), solve_set_smem_2(int), solve_set_smem_3(int), solve_set_smem_4(int), solve_set_smem_5(int);
 void solve_launch_0(int, int, int, cudaStream_t, const Params&, const Settings&, const BatchArgs&, int, int);
 void solve_launch_1(int, int, int, cudaStream_t, const Params&, const Settings&, const BatchArgs&, int, int);
 void solve_launch_2(int, int, int, cudaStream_t, const Params&, const Settings&, const BatchArgs&, int, int);
 void solve_launch_3(int, int, int, cudaStream_t, const Params&, const Settings&, const BatchArgs&, int, int);
 void solve_launch_4(int, int, int, cudaStream_t, const Params&, const Settings&, const BatchArgs&, int, int);
-int solve_reg_max_threads();
+void solve_launch_5(int, int, int, cudaStream_t, const Params&, const Settings&, const BatchArgs&, int, int);
+int solve_reg_max_threads_4();
 cudaError_t rollout_set_smem_short(int), rollout_set_smem_general(int), rollout_set_smem_pair(int);
 cudaError_t rollout_occupancy_short(int, int*), rollout_occupancy_general(int, int*), rollout_occupancy_pair(int, int*);
 void rollout_launch_short(int, int, cudaStream_t, const Params&, const Settings&, const cudampc_rollout_cfg&, const RolloutArgs&);
 void rollout_launch_general(int, int, cudaStream_t, const Params&, const Settings&, const cudampc_rollout_cfg&, const RolloutArgs&);
 void rollout_launch_pair(int, int, cudaStream_t, const Params&, const Settings&, const cudampc_rollout_cfg&, const RolloutArgs&);
-cudaError_t solve_set_smem(int v, int bytes) { return v == 0 ? solve_set_smem_0(bytes) : v == 1 ? solve_set_smem_1(bytes) : v == 2 ? solve_set_smem_2(bytes) : v == 3 ? solve_set_smem_3(bytes) : solve_set_smem_4(bytes); }
+cudaError_t solve_set_smem(int v, int bytes) { return v == 0 ? solve_set_smem_0(bytes) : v == 1 ? solve_set_smem_1(bytes) : v == 2 ? solve_set_smem_2(bytes) : v == 3 ? solve_set_smem_3(bytes) : v == 4 ? solve_set_smem_4(bytes) : solve_set_smem_5(bytes); }
 void solve_launch(int v, int grid, int threads, int smem, cudaStream_t st, const Params& p, const Settings& s, const BatchArgs& a, int P, int F) {
   if (v == 0) solve_launch_0(grid, threads, smem, st, p, s, a, P, F);
   else if (v == 1) solve_launch_1(grid, threads, smem, st, p, s, a, P, F);
   else if (v == 2) solve_launch_2(grid, threads, smem, st, p, s, a, P, F);
   else if (v == 3) solve_launch_3(grid, threads, smem, st, p, s, a, P, F);
-  else solve_launch_4(grid, threads, smem, st, p, s, a, P, F);
+  else if (v == 4) solve_launch_4(grid, threads, smem, st, p, s, a, P, F);
+  else solve_launch_5(grid, threads, smem, st, p, s, a, P, F);
 }
 cudaError_t rollout_set_smem(int f, int bytes) { return f == FORM_SHORT ? rollout_set_smem_short(bytes) : f == FORM_PAIR ? rollout_set_smem_pair(bytes) : rollout_set_smem_general(bytes); }
 cudaError_t rollout_occupancy(int f, int bytes, int* n) {
@@ -388,7 +390,8 @@ int cudampc_create(const cudampc_params* params, int max_batch, int device, cuda
     h->variant = h->grp_wpp == 2 ? SOLVE_W2 : (h->form == FORM_SHORT ? SOLVE_W1_SHORT : h->form == FORM_PAIR ? SOLVE_W1_PAIR : SOLVE_W1);
     // register form (mpc_reg.h): two warps per problem, as many problems as the kernel was compiled for (256 threads: 255
     // registers; more: 168 registers)
-    if (solve_form == FORM_REG) { const int pm = solve_reg_max_threads() / 64; if (P > pm) { P = pm; h->grp_P = pm; } h->grp_wpp = 2; h->variant = SOLVE_W2_REG; }
+    if (solve_form == FORM_REG && p.N + 1 <= 32) { if (P > 8) { P = 8; h->grp_P = 8; } h->grp_wpp = 1; h->variant = SOLVE_W1_REG; }      // a lane per stage, one warp
+    else if (solve_form == FORM_REG) { const int pm = solve_reg_max_threads_4() / 64; if (P > pm) { P = pm; h->grp_P = pm; } h->grp_wpp = 2; h->variant = SOLVE_W2_REG; }
     h->grp_smem = P * (F * (int)sizeof(double) + (int)sizeof(GroupShared)) + 16;
     e = solve_set_smem(h->variant, h->grp_smem);
     if (e != cudaSuccess) { delete h; return fail(nullptr, CUDAMPC_ERR_CUDA, "CUDA failure: %s", cudaGetErrorString(e)); }

@@ -171,9 +171,11 @@ struct GroupShared {
 // temporaries of the fused pass and the sweeps fit the 255 registers without a spill (250 used).  Inlined into the driver,
 // or as a real call (callee-saved registers of the ABI), ptxas parks part of the record in local memory, which with 227 KB
 // of shared memory carved out of the L1 is slow.  `ev`: this warp owns the even stages and runs the sweeps.
-template <int STATE>
+// WPP = 2: two warps per problem (lane j of the even / odd warp owns stage 2j / 2j+1, 64-thread named barriers);
+// WPP = 1: horizons with N + 1 <= 32, one warp per problem, lane k owns stage k (parity = parity of the lane, warp barriers).
+template <int STATE, int WPP>
 __device__ __forceinline__ void reg_block_run(double* base, int N, int fpad, int xpad, double dt, const IterConst* csm, int nb,
-                                           int lane, int ev, int bar_id, unsigned long long* tags) {
+                                           int lane, int ev_warp, int bar_id, unsigned long long* tags) {
 #ifdef MPC_TIMING     // dev builds: cycles of the parts of an iteration as the even warp's lane 0 sees them (tags 20..26)
   long long tq = clock64(), tacc[7] = {0, 0, 0, 0, 0, 0, 0};
 #define MPC_BTAG(n) do { const long long now_ = clock64(); tacc[(n) - 20] += now_ - tq; tq = now_; } while (0)
@@ -185,7 +187,9 @@ __device__ __forceinline__ void reg_block_run(double* base, int N, int fpad, int
   const volatile IterConst& c = *csm;          // read where used (see mpc_pair.h: pair_stage)
   Params p;
   p.dt = dt; p.N = N;
-  const int k = 2 * lane + (ev ? 0 : 1);
+  const int k = WPP == 2 ? 2 * lane + (ev_warp ? 0 : 1) : lane;
+  const bool ev = WPP == 2 ? ev_warp != 0 : !(lane & 1);          // this lane owns an even stage
+  const bool sweeper = WPP == 2 ? ev_warp != 0 : true;              // this warp runs the sweeps (its lanes 0..11)
   const bool on = k <= N;
   // every word defined here: a register that is read without a definition on some path (the lanes beyond the horizon) is
   // live from the kernel's entry, i.e. across the driver's code as well
@@ -202,14 +206,14 @@ __device__ __forceinline__ void reg_block_run(double* base, int N, int fpad, int
   // One loop for both warp roles: the update and the right-hand side are ONE copy of code shared by the two warps (two
   // loops - one per role - measured slower with early polish: the iteration loop competes for the 32 KB instruction cache
   // with the polish code other resident problems run).
-#define MPC_BAR() asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory")
+#define MPC_BAR() do { if (WPP == 2) asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); else __syncwarp(); } while (0)
 #pragma unroll 1
   for (int i = 0; i < nb; ++i) {
     MPC_BTAG(26);
-    if (ev) {
+    if (sweeper) {
       oe_forward_lanes(lane, w, oe);
       MPC_BTAG(20);
-      if (on) oe_diag_stage(w, oe, k);
+      if (ev && on) oe_diag_stage(w, oe, k);
       __syncwarp();
       MPC_BTAG(21);
       oe_backward_lanes(lane, w, oe);
@@ -227,14 +231,14 @@ __device__ __forceinline__ void reg_block_run(double* base, int N, int fpad, int
     MPC_BAR();                                        // B_d: t_o
     MPC_BTAG(25);
     if (ev && on) reg_fixup(w, p, c, k, T);
-    if (ev) __syncwarp();
+    if (sweeper) __syncwarp();
   }
 #ifdef MPC_TIMING
-  if (ev && lane == 0 && tags) for (int q = 0; q < 7; ++q) atomicAdd(&tags[20 + q], (unsigned long long)tacc[q]);
+  if (sweeper && lane == 0 && tags) for (int q = 0; q < 7; ++q) atomicAdd(&tags[20 + q], (unsigned long long)tacc[q]);
 #endif
-  asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+  MPC_BAR();
   if (on) reg_store<STATE>(w, k, R);
-  asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+  MPC_BAR();
 }
 
 template <int WPP>
@@ -368,7 +372,7 @@ struct GroupExec {
   // ---- register form of the iterations (mpc_reg.h): two warps per problem, the chain warp owns the even stages and runs
   // the sweeps, the other warp the odd stages; lane j <-> stage 2j (+1).  nb iterations, then the records are written back.
   __device__ __forceinline__ void admm_block(const View& w, const Params& p, const IterConst& c, const OEView&, int nb) {
-    static_assert(WPP == 2, "register form: two warps per problem");     // generic path (state in the records); the product kernel is mpc_solve_reg_kernel
+    // generic path (state in the records); the product kernels are mpc_solve_reg_kernel<.., WPP>
     if (gl() == 0) sh->drv.ic = c;
     group_sync();
 #ifdef MPC_TIMING
@@ -376,7 +380,7 @@ struct GroupExec {
 #else
     unsigned long long* tg = nullptr;
 #endif
-    reg_block_run<0>(w.base, w.N, w.fpad, w.xpad, p.dt, &sh->drv.ic, nb, lane, chain_warp() ? 1 : 0, 1 + grp(), tg);
+    reg_block_run<0, WPP>(w.base, w.N, w.fpad, w.xpad, p.dt, &sh->drv.ic, nb, lane, chain_warp() ? 1 : 0, 1 + grp(), tg);
   }
   __device__ __forceinline__ void factor(const View& w) {
     if (chain_warp()) factor_twisted_lanes(lane, w, 0, max(half_top(w.N), half_bot(w.N)), true);

@@ -79,16 +79,18 @@ __device__ __forceinline__ ProblemIO batch_io(const BatchArgs& a, int b, int N, 
   return io;
 }
 struct RegCtx { const Params* p; const Settings* s; const BatchArgs* a; double* base; GroupShared* sh; int N, fpad, xpad, lane, warp, group; };
-__device__ __forceinline__ GroupExec<2> reg_exec(const RegCtx& c) {
-  GroupExec<2> ex{c.lane, c.warp, c.sh};
+template <int WPP>
+__device__ __forceinline__ GroupExec<WPP> reg_exec(const RegCtx& c) {
+  GroupExec<WPP> ex{c.lane, c.warp, c.sh};
 #ifdef MPC_TIMING
   ex.tags = c.a->tags;
 #endif
   return ex;
 }
+template <int WPP>
 __device__ __forceinline__ void reg_drv_begin(RegCtx c, int b) {
   const View w{c.base, c.N, c.fpad, c.xpad};
-  GroupExec<2> ex = reg_exec(c);
+  GroupExec<WPP> ex = reg_exec<WPP>(c);
   const ProblemIO io = batch_io(*c.a, b, c.N, c.group);
   Drv d;
   drv_begin(ex, w, *c.p, *c.s, io, d);
@@ -96,9 +98,10 @@ __device__ __forceinline__ void reg_drv_begin(RegCtx c, int b) {
   if (ex.gl() == 0) c.sh->drv = d;
   ex.group_sync();
 }
+template <int WPP>
 __device__ __forceinline__ void reg_drv_after(RegCtx c, int b) {
   const View w{c.base, c.N, c.fpad, c.xpad};
-  GroupExec<2> ex = reg_exec(c);
+  GroupExec<WPP> ex = reg_exec<WPP>(c);
   const ProblemIO io = batch_io(*c.a, b, c.N, c.group);
   Drv d = c.sh->drv;
   ex.group_sync();                          // every lane has its copy before lane 0 writes the new one
@@ -107,24 +110,25 @@ __device__ __forceinline__ void reg_drv_after(RegCtx c, int b) {
   if (ex.gl() == 0) c.sh->drv = d;
   ex.group_sync();
 }
+template <int WPP>
 __device__ __forceinline__ void reg_drv_finish(RegCtx c, int b) {
   const View w{c.base, c.N, c.fpad, c.xpad};
-  GroupExec<2> ex = reg_exec(c);
+  GroupExec<WPP> ex = reg_exec<WPP>(c);
   const ProblemIO io = batch_io(*c.a, b, c.N, c.group);
   const Drv d = c.sh->drv;
   drv_finish(ex, w, io, d);
   ex.group_sync();
 }
-template <int MAXT, int STATE>
+template <int MAXT, int STATE, int WPP>
 __global__ void __launch_bounds__(MAXT, 1) mpc_solve_reg_kernel(const __grid_constant__ Params p, const __grid_constant__ Settings s,
                                                                 const __grid_constant__ BatchArgs a, int P, int F) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int N = p.N;
-  GroupShared* sh = reinterpret_cast<GroupShared*>(smem + (size_t)P * F) + warp / 2;
+  GroupShared* sh = reinterpret_cast<GroupShared*>(smem + (size_t)P * F) + warp / WPP;
   int fpad, xpad; layout_pads(N, fpad, xpad);
-  double* base = smem + (size_t)(warp / 2) * F;
-  GroupExec<2> ex{lane, warp, sh};
+  double* base = smem + (size_t)(warp / WPP) * F;
+  GroupExec<WPP> ex{lane, warp, sh};
   const int ev = ex.chain_warp() ? 1 : 0, bar_id = 1 + ex.grp();
 #ifdef MPC_TIMING
   unsigned long long* tg = a.tags;
@@ -134,14 +138,14 @@ __global__ void __launch_bounds__(MAXT, 1) mpc_solve_reg_kernel(const __grid_con
   for (int b = ex.fetch(a.counter); b < a.batch; b = ex.fetch(a.counter)) {
     // The pieces of the driver are inlined; none of their values is alive across a block (Drv lives in shared memory
     // between them).
-    const RegCtx c{&p, &s, &a, base, sh, N, fpad, xpad, lane, warp, (int)blockIdx.x * P + warp / 2};
-    reg_drv_begin(c, b);
+    const RegCtx c{&p, &s, &a, base, sh, N, fpad, xpad, lane, warp, (int)blockIdx.x * P + warp / WPP};
+    reg_drv_begin<WPP>(c, b);
     while (!*(volatile int*)&sh->drv.finished) {
       const int nb = *(volatile int*)&sh->drv.nb;
-      reg_block_run<STATE>(base, N, fpad, xpad, p.dt, &sh->drv.ic, nb, lane, ev, bar_id, tg);
-      reg_drv_after(c, b);
+      reg_block_run<STATE, WPP>(base, N, fpad, xpad, p.dt, &sh->drv.ic, nb, lane, ev, bar_id, tg);
+      reg_drv_after<WPP>(c, b);
     }
-    reg_drv_finish(c, b);
+    reg_drv_finish<WPP>(c, b);
   }
 }
 
@@ -271,7 +275,7 @@ __global__ void __launch_bounds__(32) mpc_rollout_kernel(Params p, Settings s, c
 // ------------------------------------------------------------------------------------------------
 // K_solve: one warp per problem with the short (N+1 <= 32), pair (N+1 <= 64) or general form of the phases, two warps per
 // problem (general form, long horizons); K_rollout: one warp per vehicle, any of the three forms (mpc_solve.h FORM_*).
-enum SolveVariant { SOLVE_W1_SHORT = 0, SOLVE_W1 = 1, SOLVE_W2 = 2, SOLVE_W1_PAIR = 3, SOLVE_W2_REG = 4 };
+enum SolveVariant { SOLVE_W1_SHORT = 0, SOLVE_W1 = 1, SOLVE_W2 = 2, SOLVE_W1_PAIR = 3, SOLVE_W2_REG = 4, SOLVE_W1_REG = 5 };
 cudaError_t solve_set_smem(int variant, int bytes);
 void solve_launch(int variant, int grid, int threads, int smem, cudaStream_t st, const Params& p, const Settings& s, const BatchArgs& a, int P, int F);
 cudaError_t rollout_set_smem(int form, int bytes);

@@ -12,12 +12,12 @@
   void solve_launch_##n(int grid, int threads, int smem, cudaStream_t st, const Params& p, const Settings& s, const BatchArgs& a, int P, int F) { \
     mpc_solve_kernel<__VA_ARGS__><<<grid, threads, smem, st>>>(p, s, a, P, F);                                                \
   }
-#define SOLVE_REG_TU(n, MAXT, STATE)                                                                                         \
-  cudaError_t solve_set_smem_##n(int bytes) { return cudaFuncSetAttribute(mpc_solve_reg_kernel<MAXT, STATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); } \
+#define SOLVE_REG_TU(n, MAXT, STATE, WPP)                                                                                         \
+  cudaError_t solve_set_smem_##n(int bytes) { return cudaFuncSetAttribute(mpc_solve_reg_kernel<MAXT, STATE, WPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); } \
   void solve_launch_##n(int grid, int threads, int smem, cudaStream_t st, const Params& p, const Settings& s, const BatchArgs& a, int P, int F) { \
-    mpc_solve_reg_kernel<MAXT, STATE><<<grid, threads, smem, st>>>(p, s, a, P, F);                                            \
+    mpc_solve_reg_kernel<MAXT, STATE, WPP><<<grid, threads, smem, st>>>(p, s, a, P, F);                                            \
   }                                                                                                                          \
-  int solve_reg_max_threads() { return MAXT; }
+  int solve_reg_max_threads_##n() { return MAXT; }
 #define ROLLOUT_TU(name, FORM)                                                                                               \
   cudaError_t rollout_set_smem_##name(int bytes) { return cudaFuncSetAttribute(mpc_rollout_kernel<FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); } \
   cudaError_t rollout_occupancy_##name(int bytes, int* n) { return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, mpc_rollout_kernel<FORM>, 32, bytes); } \
@@ -40,7 +40,9 @@ SOLVE_TU(3, 256, 1, FORM_PAIR)
 #elif MPC_TU == 6
 ROLLOUT_TU(pair, FORM_PAIR)
 #elif MPC_TU == 7
-SOLVE_REG_TU(4, MPC_REG_MAXT, MPC_REG_STATE)
+SOLVE_REG_TU(4, MPC_REG_MAXT, MPC_REG_STATE, 2)
+#elif MPC_TU == 8
+SOLVE_REG_TU(5, 256, MPC_REG_STATE, 1)
 #else
-#error "MPC_TU must be 0..7"
+#error "MPC_TU must be 0..8"
 #endif
