@@ -2,9 +2,10 @@
 //
 // The register form keeps every stage record in registers across a block of ADMM iterations.  That only works if the
 // iteration block is compiled at the TOP LEVEL of the kernel with nothing else alive: inlined into solve_problem the
-// driver's own state (settings, residuals, counters, pointers) competes for the 255 registers, and as a real function call
-// the ABI's callee-saved registers do (ptxas then parks part of the record in local memory - measured: 120k instead of
-// 260k solves/s).  So the driver is cut at the block boundary into pieces that keep ALL their state in one struct (Drv):
+// driver's own state (settings, residuals, counters, pointers) is alive across the block and competes for the 255 registers,
+// and as a real function call the ABI's register conventions do (ptxas then parks part of the record in local memory -
+// measured: 120k instead of 260k solves/s).  So the driver is cut at the block boundary into pieces that keep ALL their state
+// in one struct (Drv):
 //
 //   drv_begin    load + linearise, initial iterate
 //   drv_prepare  (re)factorise if needed, first right-hand side after a factorisation, length of the next block
@@ -12,8 +13,9 @@
 //   drv_after    termination check, early / final polish, rho adaptation            (-> d.finished)
 //   drv_finish   outputs
 //
-// The kernel calls the pieces through noinline wrappers that load Drv from shared memory and store it back; the host
-// emulation (and solve_problem<FORM_REG>) runs them back to back on a local Drv.  The logic is that of solve_problem
+// The kernel (mpc_kernels.cuh: mpc_solve_reg_kernel) inlines the pieces through wrappers that load Drv from shared memory and
+// store it back, so that no value of a piece is alive in the block; the host emulation (and solve_problem<FORM_REG>) runs
+// them back to back on a local Drv.  The logic is that of solve_problem
 // statement by statement (tests/test_emulation.py holds the two bit-identical, early polish and retries included).
 #pragma once
 #include "mpc_solve.h"

@@ -1,11 +1,11 @@
-// mpc_reg.h — the "register" form of the ADMM iterations: every stage is owned by ONE lane that keeps the stage's record
-// (ADMM state, s-tilde, linearisation, linear cost: the 46 doubles of mpc_core.h's stage record) in REGISTERS for a whole
+// mpc_reg.h — the "register" form of the ADMM iterations: every stage is owned by ONE lane that keeps the stage's state
+// (x/u, slacks, merged row states, dynamics duals, s-tilde: 35 doubles of mpc_core.h's stage record) in REGISTERS for a whole
 // block of iterations (up to the next termination check / rho adaptation).  Two warps per problem: one owns the even
-// stages (and runs the sweeps over them), the other the odd stages.
+// stages (and runs the sweeps over them), the other the odd stages; for N + 1 <= 32 also one warp with a lane per stage.
 //
-// Why: with the records in shared memory an iteration moved ~200 KB per problem through the shared-memory pipe (ncu: 53 % of
-// its peak over the whole launch, `short_scoreboard` the top stall next to the fixed-latency `wait`): the phases re-read and
-// re-write every record twice per iteration.  Here shared memory only carries what crosses lanes, one 6-double row each:
+// Why: with the records in shared memory an iteration moved 1,811 wavefronts (~200 KB) per problem through the shared-memory
+// pipe (ncu: 53 % of its peak over the whole launch, 84 % in steady state): the phases re-read and re-write every record four
+// times per iteration.  Here shared memory only carries what crosses lanes, one 6-double row each:
 //
 //   sweeps (even warp)                                x~_e -> row nx(e)
 //   B_a  T1  odd : x~_o = t_o - D_o^-1 (E_o x~_{o-1} + E_{o+1}' x~_{o+1})            -> row nx(o)
