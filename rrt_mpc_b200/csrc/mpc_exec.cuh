@@ -348,12 +348,13 @@ struct GroupExec {
   __device__ __forceinline__ void pair_pass(const View& w, const Params& p, const IterConst& c, const OEView& oe) {
     const unsigned full = 0xffffffffu;
     const bool on = lane < pair_lanes(w.N);
-    PairCtx cx;
+    PairCtx cx;        // every word defined on every path (a register read without a definition is live from the kernel's entry)
 #pragma unroll
-    for (int j = 0; j < 6; ++j) { cx.xo[j] = 0.0; cx.t[j] = 0.0; }
+    for (int j = 0; j < 6; ++j) { cx.xe[j] = 0.0; cx.xo[j] = 0.0; cx.xn[j] = 0.0; cx.be[j] = 0.0; cx.bo[j] = 0.0; cx.t[j] = 0.0; }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) cx.dd[j] = 0.0;
-    cx.Ge[3] = cx.Ge[4] = 0.0;
+    for (int j = 0; j < 4; ++j) { cx.de[j] = 0.0; cx.dd[j] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { cx.Ge[j] = 0.0; cx.Go[j] = 0.0; }
     if (on) pair_expand(w, p, c, oe, lane, cx);
     double ua = __shfl_up_sync(full, cx.xo[4], 1), ud = __shfl_up_sync(full, cx.xo[5], 1);
     if (lane == 0) { ua = 0.0; ud = 0.0; }
