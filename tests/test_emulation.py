@@ -243,3 +243,55 @@ def test_saved_factor_equals_refactorisation_on_resume():
         for k in ("u0", "Xp", "Up", "iters", "status"):
             assert np.array_equal(a[k], b[k]), k
         assert a["info"][:, 1].sum() < b["info"][:, 1].sum()          # fewer factorisations
+
+
+@pytest.mark.parametrize("kw", [
+    dict(check_termination=10, adaptive_rho_interval=35),            # events of the two kinds interleave: 10, 20, 30, 35, 40, ...
+    dict(max_iter=73, polish_passes=1),                              # iteration limit inside a block, status from the 10x looser test
+    dict(check_termination=25, adaptive_rho_interval=0),             # 0 = the library's fixed default interval
+    dict(adaptive_rho=0, max_iter=400),                              # no rho adaptation at all
+    dict(polish_passes=0),                                           # no polish: the raw ADMM iterate is the answer
+])
+def test_register_form_block_schedule_matches_the_iteration_loop(kw):
+    """The register form runs the iterations in blocks that end at the next event (termination check, rho adaptation, iteration
+    limit; mpc_drv.h: drv_prepare).  Whatever the schedule of events, status, iteration counts, rho updates and results must be
+    those of the form that tests after every iteration."""
+    g = load_golden("optima.npz")
+    for name, N, du in (("n20", 20, 0.15), ("n50", 50, 0.02)):
+        p = oracle_params(N, du)
+        nb = 5
+        s = dict(polish_passes=3, polish_retry=1, early_polish=1, **TIGHT)
+        s.update(kw)
+        try:
+            E.set_form(3)
+            a = E.solve(p, g[f"{name}_x0"][:nb], g[f"{name}_ref"][:nb], g[f"{name}_up"][:nb], **s)
+            E.set_form(0)
+            b = E.solve(p, g[f"{name}_x0"][:nb], g[f"{name}_ref"][:nb], g[f"{name}_up"][:nb], **s)
+        finally:
+            E.set_form(-1)
+        for k in ("status", "iters", "info", "u0", "Xp", "Up", "pri", "dua"):
+            assert np.array_equal(a[k], b[k]), (kw, name, k)
+
+
+def test_register_form_warm_start_and_slot_state():
+    """Warm start through the register form: the iterate stored by one solve is the starting point of the next (same slot), and
+    the stored iterate itself equals the one the general form stores."""
+    g = load_golden("optima.npz")
+    p = oracle_params(20)
+    nb = 6
+    kw = dict(polish_passes=3, **TIGHT)
+    outs = {}
+    for form in (3, 0):
+        try:
+            E.set_form(form)
+            warm = np.zeros((nb, E.warm_size(20)))
+            cold = E.solve(p, g["n20_x0"][:nb], g["n20_ref"][:nb], g["n20_up"][:nb], warm=warm, warm_start=0, **kw)
+            hot = E.solve(p, g["n20_x0"][:nb] + 0.01, g["n20_ref"][:nb], g["n20_up"][:nb], warm=warm, warm_start=1, **kw)
+        finally:
+            E.set_form(-1)
+        outs[form] = (cold, hot, warm.copy())
+    for i in (0, 1):
+        for k in ("status", "iters", "u0", "Xp", "Up"):
+            assert np.array_equal(outs[3][i][k], outs[0][i][k]), (i, k)
+    assert np.array_equal(outs[3][2], outs[0][2])
+    assert outs[3][1]["iters"].sum() < outs[3][0]["iters"].sum()
