@@ -379,8 +379,13 @@ int cudampc_create(const cudampc_params* params, int max_batch, int device, cuda
   // latency-bound there); at P >= 3 the extra barriers cost more than the second warp saves (measured again in round 2:
   // branch item-form-experiment).
   {
-    int solve_form = h->form;                                         // K_solve may run the register form (K_rollout: one warp)
-    if (const char* fe = getenv("CUDAMPC_FORM")) { if (!strcmp(fe, "reg") && p.N + 1 <= 64) solve_form = FORM_REG; }
+    // K_solve: horizons with 32 < N+1 <= 64 run the two-warp register form (mpc_reg.h; 279 k / 369 k solves/s against 268 k / 364 k for
+    // the one-warp parity form at horizon 50); CUDAMPC_FORM=reg selects it for short horizons too, general / pair / short override it
+    int solve_form = (p.N + 1 > 32 && p.N + 1 <= 64) ? FORM_REG : h->form;
+    if (const char* fe = getenv("CUDAMPC_FORM")) {
+      if (!strcmp(fe, "reg") && p.N + 1 <= 64) solve_form = FORM_REG;
+      else if (!strcmp(fe, "general") || !strcmp(fe, "pair") || !strcmp(fe, "short")) solve_form = h->form;
+    }
     int P = (optin - 64) / (F * (int)sizeof(double) + (int)sizeof(GroupShared));
     if (P > 8) P = 8;
     if (const char* pe = getenv("CUDAMPC_P")) { int v = atoi(pe); if (v >= 1 && v < P) P = v; }   // tuning knobs

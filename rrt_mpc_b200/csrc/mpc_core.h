@@ -964,34 +964,34 @@ MPC_HD void bx_load6(const View& w, int k, double* x) {
 // A1: consume x-tilde / s-tilde, relax x and s, update the row states.  xt = x-tilde of stage k, xn = of stage k+1 (read
 // when k < N), (ua, ud) = the inputs of stage k-1 (0 for k = 0).
 MPC_HD void admm_update_vals(const View& w, const Params& p, const IterConst& c, int k, const double* xt, const double* xn, double ua, double ud) {
+  // Branch-free over the groups and the terminal stage (see mpc_pair.h: pair_stage): the unused slots of the terminal record hold
+  // exact zeros, a fixed point of the update, so the one terminal lane computes them like a regular stage and the compiler gets the
+  // five groups, the dynamics rows and the relaxation as ONE basic block.  Only the dynamics duals and the inputs need a select.
   const int N = w.N;
   double* rc = w.rec(k);
   const bool reg = k < N;
   const double off0 = k == 0 ? c.up0 : 0.0, off1 = k == 0 ? c.up1 : 0.0;
-  const double gt[5] = {xt[3], xt[4], xt[5], xt[4] - ua, xt[5] - ud};
+  const double gt[5] = {xt[3], reg ? xt[4] : 0.0, reg ? xt[5] : 0.0, reg ? xt[4] - ua : 0.0, reg ? xt[5] - ud : 0.0};
   const double offs[5] = {0.0, 0.0, 0.0, off0, off1};
 #pragma unroll
   for (int g = 0; g < 5; ++g) {
-    if (g == 0 || reg) {
-      const double st = rc[R_ST + g], sv = rc[R_S + g];
-      const double v0 = rc[R_V + 3 * g], v1 = rc[R_V + 3 * g + 1], v2 = rc[R_V + 3 * g + 2];
-      const double z0 = dmin2(v0, c.hi[g] + offs[g]), z1 = dmax2(v1, c.lo[g] + offs[g]), z2 = dmax2(v2, 0.0);
-      rc[R_V + 3 * g] = fma(c.alpha, (gt[g] - st) - z0, v0);
-      rc[R_V + 3 * g + 1] = fma(c.alpha, (gt[g] + st) - z1, v1);
-      rc[R_V + 3 * g + 2] = fma(c.alpha, st - z2, v2);
-      rc[R_S + g] = fma(c.alpha, st - sv, sv);
-    }
+    const double st = rc[R_ST + g], sv = rc[R_S + g];
+    const double v0 = rc[R_V + 3 * g], v1 = rc[R_V + 3 * g + 1], v2 = rc[R_V + 3 * g + 2];
+    const double z0 = dmin2(v0, c.hi[g] + offs[g]), z1 = dmax2(v1, c.lo[g] + offs[g]), z2 = dmax2(v2, 0.0);
+    rc[R_V + 3 * g] = fma(c.alpha, (gt[g] - st) - z0, v0);
+    rc[R_V + 3 * g + 1] = fma(c.alpha, (gt[g] + st) - z1, v1);
+    rc[R_V + 3 * g + 2] = fma(c.alpha, st - z2, v2);
+    rc[R_S + g] = fma(c.alpha, st - sv, sv);
   }
-  if (reg) {
+  {
     const double* lin = rc + R_LIN;
     const double z0 = xn[0] - (xt[0] + lin[0] * xt[2] + lin[1] * xt[3]);
     const double z1 = xn[1] - (xt[1] + lin[2] * xt[2] + lin[3] * xt[3]);
     const double z2 = xn[2] - (xt[2] + lin[4] * xt[5]);
     const double z3 = xn[3] - (xt[3] + p.dt * xt[4]);
-    rc[R_YE + 0] = fma(c.ra, z0 - lin[5], rc[R_YE + 0]);
-    rc[R_YE + 1] = fma(c.ra, z1 - lin[6], rc[R_YE + 1]);
-    rc[R_YE + 2] = fma(c.ra, z2, rc[R_YE + 2]);
-    rc[R_YE + 3] = fma(c.ra, z3, rc[R_YE + 3]);
+    const double y0 = fma(c.ra, z0 - lin[5], rc[R_YE + 0]), y1 = fma(c.ra, z1 - lin[6], rc[R_YE + 1]);
+    const double y2 = fma(c.ra, z2, rc[R_YE + 2]), y3 = fma(c.ra, z3, rc[R_YE + 3]);
+    rc[R_YE + 0] = reg ? y0 : 0.0; rc[R_YE + 1] = reg ? y1 : 0.0; rc[R_YE + 2] = reg ? y2 : 0.0; rc[R_YE + 3] = reg ? y3 : 0.0;
   }
   if (k == 0) {
     double* h = w.hdr();
@@ -999,59 +999,59 @@ MPC_HD void admm_update_vals(const View& w, const Params& p, const IterConst& c,
     for (int r = 0; r < 4; ++r) h[H_YI + r] = fma(c.ra, xt[r] - h[H_X0 + r], h[H_YI + r]);
   }
 #pragma unroll
-  for (int j = 0; j < 6; ++j)
-    if (j < 4 || reg) { const double xo = rc[R_XU + j]; rc[R_XU + j] = fma(c.alpha, xt[j] - xo, xo); }
+  for (int j = 0; j < 6; ++j) {
+    const double xo = rc[R_XU + j];
+    const double xw = fma(c.alpha, xt[j] - xo, xo);
+    rc[R_XU + j] = (j < 4 || reg) ? xw : 0.0;
+  }
 }
 
 // A2: t = rho z - y of every row from the new state, s-tilde, right-hand side of stage k -> val[6]
 MPC_HD void admm_rhs_vals(const View& w, const Params& p, const IterConst& c, int k, double* val) {
+  // branch-free like A1: for the terminal stage G[1..4], its dynamics duals and lin are exact zeros, so its terms vanish; the
+  // neighbours' records are read through clamped indices and selected
   const int N = w.N;
   double* rc = w.rec(k);
   const bool reg = k < N;
   const double off0 = k == 0 ? c.up0 : 0.0, off1 = k == 0 ? c.up1 : 0.0;
   const double offs[5] = {0.0, 0.0, 0.0, off0, off1};
-  double G[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  double G[5];
 #pragma unroll
   for (int g = 0; g < 5; ++g) {
-    if (g == 0 || reg) {
-      const double v0 = rc[R_V + 3 * g], v1 = rc[R_V + 3 * g + 1], v2 = rc[R_V + 3 * g + 2];
-      const double z0 = dmin2(v0, c.hi[g] + offs[g]), z1 = dmax2(v1, c.lo[g] + offs[g]), z2 = dmax2(v2, 0.0);
-      const double t0 = c.rho * (z0 + (z0 - v0)), t1 = c.rho * (z1 + (z1 - v1)), t2 = c.rho * (z2 + (z2 - v2));
-      rc[R_ST + g] = (c.sigma * rc[R_S + g] + ((t1 - t0) + t2)) * c.mssinv[g];
-      G[g] = t0 + t1;
-    }
+    const double v0 = rc[R_V + 3 * g], v1 = rc[R_V + 3 * g + 1], v2 = rc[R_V + 3 * g + 2];
+    const double z0 = dmin2(v0, c.hi[g] + offs[g]), z1 = dmax2(v1, c.lo[g] + offs[g]), z2 = dmax2(v2, 0.0);
+    const double t0 = c.rho * (z0 + (z0 - v0)), t1 = c.rho * (z1 + (z1 - v1)), t2 = c.rho * (z2 + (z2 - v2));
+    rc[R_ST + g] = (c.sigma * rc[R_S + g] + ((t1 - t0) + t2)) * c.mssinv[g];
+    G[g] = t0 + t1;
   }
   double out[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  if (k >= 1) {
-    const double* rp = w.rec(k - 1);
-    out[0] = c.rho_eq * rp[R_LIN + 5] - rp[R_YE + 0];
-    out[1] = c.rho_eq * rp[R_LIN + 6] - rp[R_YE + 1];
-    out[2] = -rp[R_YE + 2];
-    out[3] = -rp[R_YE + 3];
-  } else {
+  {
+    const double* rp = w.rec(k >= 1 ? k - 1 : 0);
     const double* h = w.hdr();
-#pragma unroll
-    for (int r = 0; r < 4; ++r) out[r] = c.rho_eq * h[H_X0 + r] - h[H_YI + r];
+    const double p0 = c.rho_eq * rp[R_LIN + 5] - rp[R_YE + 0], p1 = c.rho_eq * rp[R_LIN + 6] - rp[R_YE + 1];
+    const double p2 = -rp[R_YE + 2], p3 = -rp[R_YE + 3];
+    const double i0_ = c.rho_eq * h[H_X0 + 0] - h[H_YI + 0], i1_ = c.rho_eq * h[H_X0 + 1] - h[H_YI + 1];
+    const double i2_ = c.rho_eq * h[H_X0 + 2] - h[H_YI + 2], i3_ = c.rho_eq * h[H_X0 + 3] - h[H_YI + 3];
+    out[0] = k >= 1 ? p0 : i0_; out[1] = k >= 1 ? p1 : i1_; out[2] = k >= 1 ? p2 : i2_; out[3] = k >= 1 ? p3 : i3_;
   }
   out[3] += G[0];
-  if (reg) {
+  {
     const double* lin = rc + R_LIN;
-    const double d0 = c.rho_eq * lin[5] - rc[R_YE + 0], d1 = c.rho_eq * lin[6] - rc[R_YE + 1];
-    const double d2 = -rc[R_YE + 2], d3 = -rc[R_YE + 3];
+    const double d0 = reg ? c.rho_eq * lin[5] - rc[R_YE + 0] : 0.0, d1 = reg ? c.rho_eq * lin[6] - rc[R_YE + 1] : 0.0;
+    const double d2 = reg ? -rc[R_YE + 2] : 0.0, d3 = reg ? -rc[R_YE + 3] : 0.0;
     out[0] -= d0;
     out[1] -= d1;
     out[2] -= lin[0] * d0 + lin[2] * d1 + d2;
     out[3] -= lin[1] * d0 + lin[3] * d1 + d3;
     out[4] = G[1] + G[3] - p.dt * d3;
     out[5] = G[2] + G[4] - lin[4] * d2;
-    if (k + 1 < N) {
-      const double* rn = w.rec(k + 1);
+    const double* rn = w.rec(k + 1 <= N ? k + 1 : N);                  // rate groups of stage k+1 (zeros at the terminal stage)
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const double v0 = rn[R_V + 3 * (3 + i)], v1 = rn[R_V + 3 * (3 + i) + 1];
-        const double z0 = dmin2(v0, c.hi[3 + i]), z1 = dmax2(v1, c.lo[3 + i]);
-        out[4 + i] -= c.rho * (z0 + (z0 - v0)) + c.rho * (z1 + (z1 - v1));
-      }
+    for (int i = 0; i < 2; ++i) {
+      const double v0 = rn[R_V + 3 * (3 + i)], v1 = rn[R_V + 3 * (3 + i) + 1];
+      const double z0 = dmin2(v0, c.hi[3 + i]), z1 = dmax2(v1, c.lo[3 + i]);
+      const double rsum = c.rho * (z0 + (z0 - v0)) + c.rho * (z1 + (z1 - v1));
+      out[4 + i] -= (k + 1 < N) ? rsum : 0.0;
     }
   }
 #pragma unroll

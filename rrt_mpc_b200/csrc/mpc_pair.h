@@ -73,49 +73,54 @@ template <class C>
 // (in, out) or, in the register form with partial residency, the shared-memory record while (in, out) is the register copy.
 MPC_HD void pair_stage(const double* __restrict__ in, double* __restrict__ out, const double* inx, double* outx, const double* cst, double* hdr,
                        const Params& p, const C& c, int N, int k, const double* xt, const double* xn, double ua, double ud, double* G) {
+  // BRANCH-FREE over the groups and the terminal stage: the terminal stage has no inputs, no dynamics rows and only the velocity
+  // group, but its record has the slots of a regular stage and they hold exact zeros (cold_start_stage), which are a fixed point of
+  // the update (z = clip(0) = 0 inside the bounds, n = 0 + alpha (0 - 0) = 0, t = 0, G = 0): computing them costs the one terminal
+  // lane nothing extra and lets the compiler schedule the five groups, the dynamics rows and the relaxation as ONE basic block
+  // (with a branch per group the phases were ~12 dependent fp64 operations at a time: `wait` 1.5 stall cycles per instruction).
+  // Only the dynamics duals and the input entries need a select.
   const bool reg = k < N;
   const double c_ra = c.ra, c_alpha = c.alpha, c_rho = c.rho, c_sigma = c.sigma;
-  if (reg) {
+  {
     const double* lin = cst + R_LIN;
     const double z0 = xn[0] - (xt[0] + lin[0] * xt[2] + lin[1] * xt[3]);
     const double z1 = xn[1] - (xt[1] + lin[2] * xt[2] + lin[3] * xt[3]);
     const double z2 = xn[2] - (xt[2] + lin[4] * xt[5]);
     const double z3 = xn[3] - (xt[3] + p.dt * xt[4]);
-    outx[R_YE + 0] = fma(c_ra, z0 - lin[5], inx[R_YE + 0]);
-    outx[R_YE + 1] = fma(c_ra, z1 - lin[6], inx[R_YE + 1]);
-    outx[R_YE + 2] = fma(c_ra, z2, inx[R_YE + 2]);
-    outx[R_YE + 3] = fma(c_ra, z3, inx[R_YE + 3]);
+    const double y0 = fma(c_ra, z0 - lin[5], inx[R_YE + 0]), y1 = fma(c_ra, z1 - lin[6], inx[R_YE + 1]);
+    const double y2 = fma(c_ra, z2, inx[R_YE + 2]), y3 = fma(c_ra, z3, inx[R_YE + 3]);
+    outx[R_YE + 0] = reg ? y0 : 0.0; outx[R_YE + 1] = reg ? y1 : 0.0; outx[R_YE + 2] = reg ? y2 : 0.0; outx[R_YE + 3] = reg ? y3 : 0.0;
   }
   if (k == 0) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) hdr[H_YI + r] = fma(c_ra, xt[r] - hdr[H_X0 + r], hdr[H_YI + r]);
   }
   const double off0 = k == 0 ? c.up0 : 0.0, off1 = k == 0 ? c.up1 : 0.0;
-  const double gt[5] = {xt[3], xt[4], xt[5], xt[4] - ua, xt[5] - ud};
+  const double gt[5] = {xt[3], reg ? xt[4] : 0.0, reg ? xt[5] : 0.0, reg ? xt[4] - ua : 0.0, reg ? xt[5] - ud : 0.0};
   const double offs[5] = {0.0, 0.0, 0.0, off0, off1};
 #pragma unroll
   for (int g = 0; g < 5; ++g) {
-    G[g] = 0.0;
-    if (g == 0 || reg) {
-      const double st = in[R_ST + g], sv = in[R_S + g];
-      const double v0 = in[R_V + 3 * g], v1 = in[R_V + 3 * g + 1], v2 = in[R_V + 3 * g + 2];
-      const double hi = c.hi[g] + offs[g], lo = c.lo[g] + offs[g], ms = c.mssinv[g];
-      const double z0 = dmin2(v0, hi), z1 = dmax2(v1, lo), z2 = dmax2(v2, 0.0);
-      const double n0 = fma(c_alpha, (gt[g] - st) - z0, v0);
-      const double n1 = fma(c_alpha, (gt[g] + st) - z1, v1);
-      const double n2 = fma(c_alpha, st - z2, v2);
-      const double sn = fma(c_alpha, st - sv, sv);
-      out[R_V + 3 * g] = n0; out[R_V + 3 * g + 1] = n1; out[R_V + 3 * g + 2] = n2;
-      out[R_S + g] = sn;
-      const double y0 = dmin2(n0, hi), y1 = dmax2(n1, lo), y2 = dmax2(n2, 0.0);
-      const double t0 = c_rho * (y0 + (y0 - n0)), t1 = c_rho * (y1 + (y1 - n1)), t2 = c_rho * (y2 + (y2 - n2));
-      out[R_ST + g] = (c_sigma * sn + ((t1 - t0) + t2)) * ms;
-      G[g] = t0 + t1;
-    }
+    const double st = in[R_ST + g], sv = in[R_S + g];
+    const double v0 = in[R_V + 3 * g], v1 = in[R_V + 3 * g + 1], v2 = in[R_V + 3 * g + 2];
+    const double hi = c.hi[g] + offs[g], lo = c.lo[g] + offs[g], ms = c.mssinv[g];
+    const double z0 = dmin2(v0, hi), z1 = dmax2(v1, lo), z2 = dmax2(v2, 0.0);
+    const double n0 = fma(c_alpha, (gt[g] - st) - z0, v0);
+    const double n1 = fma(c_alpha, (gt[g] + st) - z1, v1);
+    const double n2 = fma(c_alpha, st - z2, v2);
+    const double sn = fma(c_alpha, st - sv, sv);
+    out[R_V + 3 * g] = n0; out[R_V + 3 * g + 1] = n1; out[R_V + 3 * g + 2] = n2;
+    out[R_S + g] = sn;
+    const double y0 = dmin2(n0, hi), y1 = dmax2(n1, lo), y2 = dmax2(n2, 0.0);
+    const double t0 = c_rho * (y0 + (y0 - n0)), t1 = c_rho * (y1 + (y1 - n1)), t2 = c_rho * (y2 + (y2 - n2));
+    out[R_ST + g] = (c_sigma * sn + ((t1 - t0) + t2)) * ms;
+    G[g] = t0 + t1;
   }
 #pragma unroll
-  for (int j = 0; j < 6; ++j)
-    if (j < 4 || reg) { const double xo = inx[R_XU + j]; outx[R_XU + j] = fma(c_alpha, xt[j] - xo, xo); }
+  for (int j = 0; j < 6; ++j) {
+    const double xo = inx[R_XU + j];
+    const double xw = fma(c_alpha, xt[j] - xo, xo);
+    outx[R_XU + j] = (j < 4 || reg) ? xw : 0.0;
+  }
 }
 // d = rho_eq c - y of the dynamics rows of stage k (zeros for the terminal stage), from the state `st`
 template <class C>
@@ -161,18 +166,18 @@ MPC_HD void pair_update(const View& w, const Params& p, const IterConst& c, int 
 // rows), rnext = rate-group sums (G[3], G[4]) of stage k+1
 MPC_HD void pair_assemble(const double* lin, const Params& p, int N, int k, const double* dprev, const double* d, const double* G,
                           const double* rnext, const double* base, double* val) {
+  // branch-free: for the terminal stage d = 0 (stage_d), G[1..4] = 0 and lin = 0, so the terms below vanish exactly
   const bool reg = k < N;
   double out[6] = {dprev[0], dprev[1], dprev[2], dprev[3], 0.0, 0.0};
   out[3] += G[0];
-  if (reg) {
-    out[0] -= d[0];
-    out[1] -= d[1];
-    out[2] -= lin[0] * d[0] + lin[2] * d[1] + d[2];
-    out[3] -= lin[1] * d[0] + lin[3] * d[1] + d[3];
-    out[4] = G[1] + G[3] - p.dt * d[3];
-    out[5] = G[2] + G[4] - lin[4] * d[2];
-    if (k + 1 < N) { out[4] -= rnext[0]; out[5] -= rnext[1]; }
-  }
+  out[0] -= d[0];
+  out[1] -= d[1];
+  out[2] -= lin[0] * d[0] + lin[2] * d[1] + d[2];
+  out[3] -= lin[1] * d[0] + lin[3] * d[1] + d[3];
+  out[4] = G[1] + G[3] - p.dt * d[3];
+  out[5] = G[2] + G[4] - lin[4] * d[2];
+  out[4] -= (k + 1 < N) ? rnext[0] : 0.0;
+  out[5] -= (k + 1 < N) ? rnext[1] : 0.0;
 #pragma unroll
   for (int j = 0; j < 6; ++j) val[j] = (j < 4 || reg) ? base[j] + out[j] : 0.0;
 }

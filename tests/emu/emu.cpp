@@ -92,7 +92,7 @@ static void unpack(const double* par, const double* set, int N, Params& p, Setti
 
 static int g_fsave = 1;       // keep the ADMM factor in a side buffer over a polish (0: refactorise on resume)
 void emu_set_fsave(int f) { g_fsave = f; }
-static int g_form = -1;      // -1: what the library picks (short form for N+1 <= 32, pair form for N+1 <= 64), else FORM_* of mpc_solve.h
+static int g_form = -1;      // -1: what the library picks (short form for N+1 <= 32, register form for N+1 <= 64), else FORM_* of mpc_solve.h
 void emu_set_form(int f) { g_form = f & 3; g_reg_state = (f & 4) ? 0 : 1; if (f < 0) { g_form = -1; g_reg_state = 1; } }
 
 int emu_solve_batch(const double* par, const double* set, int N, int B, int reverse,
@@ -113,7 +113,7 @@ int emu_solve_batch(const double* par, const double* set, int N, int B, int reve
     Settings sb = s;
     if (!warm) sb.warm_start = 0;
     EmuExec ex{reverse};
-    const int form = g_form >= 0 ? g_form : (N + 1 <= 32 ? FORM_SHORT : (N + 1 <= 64 ? FORM_PAIR : FORM_GENERAL));
+    const int form = g_form >= 0 ? g_form : (N + 1 <= 32 ? FORM_SHORT : (N + 1 <= 64 ? FORM_REG : FORM_GENERAL));
     if (form == FORM_SHORT && N + 1 <= 32) solve_problem<FORM_SHORT>(ex, w, p, sb, io);
     else if (form == FORM_PAIR && N + 1 <= 64) solve_problem<FORM_PAIR>(ex, w, p, sb, io);
     else if (form == FORM_REG && N + 1 <= 64) solve_problem<FORM_REG>(ex, w, p, sb, io);
