@@ -72,12 +72,11 @@ MPC_HD void reg_expand(const View& w, const Params& p, const C& c, const OEView&
 #pragma unroll
   for (int j = 0; j < 6; ++j) T.xn[j] = 0.0;
   cross_mul(w.rec(k - 1) + R_LIN, p.dt, re, kap, k < N, xp, v);
-  if (k + 1 <= N) {
-    row_load(w.nx(k + 1), T.xn);
-    cross_mul_t(w.rec(k) + R_LIN, p.dt, re, kap, k + 1 < N, T.xn, y);
+  // no branch for the last stage: the row of zeros stands in for row N+1 and the terminal record's lin is zero, so the term is an exact +-0
+  row_load(k + 1 <= N ? w.nx(k + 1) : w.nx_zero(), T.xn);
+  cross_mul_t(w.rec(k) + R_LIN, p.dt, re, kap, k + 1 < N, T.xn, y);
 #pragma unroll
-    for (int j = 0; j < 6; ++j) v[j] += y[j];
-  }
+  for (int j = 0; j < 6; ++j) v[j] += y[j];
   sym_load(oe.dinv + OE_SYM * (k >> 1), di);
   symv6(di, v, u);
   double t[6];
@@ -91,11 +90,11 @@ MPC_HD void reg_expand(const View& w, const Params& p, const C& c, const OEView&
 MPC_HD void reg_gather_even(const View& w, int k, StageTmp& T) {
   const int N = w.N;
   row_load(w.nx(k), T.xt);
-#pragma unroll
-  for (int j = 0; j < 6; ++j) T.xn[j] = 0.0;
-  if (k + 1 <= N) row_load(w.nx(k + 1), T.xn);
-  T.ua = 0.0; T.ud = 0.0;
-  if (k > 0 && k < N) { const double* xp = w.nx(k - 1); T.ua = xp[4]; T.ud = xp[5]; }
+  row_load(k + 1 <= N ? w.nx(k + 1) : w.nx_zero(), T.xn);  // beyond the horizon: the row of zeros
+  const double* xp = w.nx(k > 0 ? k - 1 : 0);             // branch-free: clamped index + select
+  const double ua = xp[4], ud = xp[5];
+  const bool ib = k > 0 && k < N;
+  T.ua = ib ? ua : 0.0; T.ud = ib ? ud : 0.0;
 }
 // T2: A1 + own part of A2 on the registers, publish (d, G[3], G[4])
 template <int STATE, class C>
@@ -117,22 +116,23 @@ template <int STATE, class C>
 MPC_HD void reg_rhs(const View& w, const Params& p, const C& c, const OEView& oe, int k, StageRegs& R, StageTmp& T) {
   const int N = w.N;
   const double re = c.rho_eq, kap = c.kap;
-  double dp[4], rn[2] = {0.0, 0.0};
-  if (k == 0) {
+  // branch-free: the neighbours' values through clamped indices, then selects (stage 0: the initial-state rows)
+  double dp[4], rn[2];
+  {
     const double* h = w.hdr();
+    const int kp = k >= 1 ? k - 1 : 0, kn = k + 1 <= N ? k + 1 : N;
+    double di_[4], dm[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) dp[r] = re * h[H_X0 + r] - h[H_YI + r];
-  } else if (STATE) {
-    const double* mp = reg_mb(w, k - 1);
+    for (int r = 0; r < 4; ++r) di_[r] = re * h[H_X0 + r] - h[H_YI + r];
+    if (STATE) {
+      const double* mp = reg_mb(w, kp);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) dp[r] = mp[r];
-  } else {
-    stage_d(w.rec(k - 1), w.rec(k - 1), c, true, dp);
-  }
-  if (k + 1 < N) {
-    if (STATE) { const double* mn = reg_mb(w, k + 1); rn[0] = mn[4]; rn[1] = mn[5]; }
-    else {                                              // G[3], G[4] of stage k+1 from its row states (admm_rhs_vals)
-      const double* rnx = w.rec(k + 1);
+      for (int r = 0; r < 4; ++r) dm[r] = mp[r];
+      const double* mn = reg_mb(w, kn);
+      rn[0] = mn[4]; rn[1] = mn[5];
+    } else {
+      stage_d(w.rec(kp), w.rec(kp), c, true, dm);
+      const double* rnx = w.rec(kn);                    // G[3], G[4] of stage k+1 from its row states (admm_rhs_vals)
       const double rho = c.rho;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
@@ -141,6 +141,8 @@ MPC_HD void reg_rhs(const View& w, const Params& p, const C& c, const OEView& oe
         rn[i] = rho * (z0 + (z0 - v0)) + rho * (z1 + (z1 - v1));
       }
     }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) dp[r] = k >= 1 ? dm[r] : di_[r];
   }
   double val[6], d[4], base[6];
   const double* sx = STATE == 1 ? R.r : w.rec(k);
@@ -163,19 +165,18 @@ template <class C>
 MPC_HD void reg_fixup(const View& w, const Params& p, const C& c, int k, StageTmp& T) {
   const int N = w.N;
   const double re = c.rho_eq, kap = c.kap;
-  double t[6], y[6];
-  if (k >= 1) {
-    row_load(w.nx(k - 1), t);
-    cross_mul(w.rec(k - 1) + R_LIN, p.dt, re, kap, k < N, t, y);
+  // branch-free: stage 0 reads a clamped row and drops the term with a select; beyond the last stage the row of zeros and the
+  // terminal record's zero lin give an exact +-0
+  double t[6], y[6], t2[6], y2[6];
+  const int kp = k >= 1 ? k - 1 : 0;
+  row_load(w.nx(kp), t);
+  row_load(k + 1 <= N ? w.nx(k + 1) : w.nx_zero(), t2);
+  cross_mul(w.rec(kp) + R_LIN, p.dt, re, kap, k < N, t, y);
+  cross_mul_t(w.rec(k) + R_LIN, p.dt, re, kap, k + 1 < N, t2, y2);
 #pragma unroll
-    for (int j = 0; j < 6; ++j) T.b[j] -= y[j];
-  }
-  if (k + 1 <= N) {
-    row_load(w.nx(k + 1), t);
-    cross_mul_t(w.rec(k) + R_LIN, p.dt, re, kap, k + 1 < N, t, y);
+  for (int j = 0; j < 6; ++j) T.b[j] -= (k >= 1) ? y[j] : 0.0;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) T.b[j] -= y[j];
-  }
+  for (int j = 0; j < 6; ++j) T.b[j] -= y2[j];
   row_store(w.nx(k), T.b);
 }
 
