@@ -41,13 +41,15 @@ def test_iteration_identical_to_oracle_in_mirror_mode():
         assert np.abs(r["u0"] - c["u0"]).max() < 1e-9
 
 
-def test_early_polish_certifies_the_same_optimum():
+@pytest.mark.parametrize("check", [25, 50])      # 50 = the rho-adaptation interval: the setting bench.py runs early polish with
+def test_early_polish_certifies_the_same_optimum(check):
     g = load_golden("optima.npz")
     for name, N, du in (("n20", 20, 0.15), ("n50", 50, 0.02)):
         p = oracle_params(N, du)
         nb = 12
         lit = E.solve(p, g[f"{name}_x0"][:nb], g[f"{name}_ref"][:nb], g[f"{name}_up"][:nb], polish_passes=5, polish_retry=2, **TIGHT)
-        ear = E.solve(p, g[f"{name}_x0"][:nb], g[f"{name}_ref"][:nb], g[f"{name}_up"][:nb], polish_passes=5, polish_retry=2, early_polish=1, **TIGHT)
+        ear = E.solve(p, g[f"{name}_x0"][:nb], g[f"{name}_ref"][:nb], g[f"{name}_up"][:nb], polish_passes=5, polish_retry=2, early_polish=1,
+                      check_termination=check, **TIGHT)
         assert (ear["status"] == 1).all() and (ear["info"][:, 2] > 0).all()
         assert np.abs(ear["u0"] - g[f"{name}_u0"][:nb]).max() < 1e-8
         assert np.abs(ear["u0"] - lit["u0"]).max() < 1e-9

@@ -23,14 +23,15 @@ def kkt_check(p, x0, ref, up, r, A, Bm, c):
     return dyn, init
 
 
+@pytest.mark.parametrize("check", [25, 50])      # 50 = the rho-adaptation interval: the setting bench.py runs early polish with
 @pytest.mark.parametrize("N,B,du,seed", [(20, 4096, 0.15, 2), (50, 65536, 0.02, 3)])
-def test_full_size_batches(N, B, du, seed):
+def test_full_size_batches(N, B, du, seed, check):
     import torch
     from rrt_mpc_b200 import MPCController, SolverSettings
     from rrt_mpc_b200.synthetic import make_batch
     from oracle import mpc_numpy as O
     x0, ref, up = make_batch(B, N, seed)
-    ctl = MPCController(product_params(N, du), SolverSettings(polish_passes=5, polish_retry=4, early_polish=True, **TIGHT), max_batch=B)
+    ctl = MPCController(product_params(N, du), SolverSettings(polish_passes=5, polish_retry=4, early_polish=True, check_termination=check, **TIGHT), max_batch=B)
     d = lambda a: torch.as_tensor(a).cuda()
     dx0, dref, dup = d(x0), d(ref), d(up)
     rd = ctl.solve_batch(dx0, dref, u_prev=dup)

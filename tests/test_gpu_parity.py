@@ -68,11 +68,12 @@ def test_status_and_iterations_identical_to_oracle(name, N, du):
     assert np.abs(r3.u0 - o["u0"]).max() < 1e-5
 
 
+@pytest.mark.parametrize("check", [25, 50])      # 50 = the rho-adaptation interval: the setting bench.py runs early polish with
 @pytest.mark.parametrize("name,N,du", [("n20", 20, 0.15), ("n50", 50, 0.02)])
-def test_early_polish_same_optimum_fewer_iterations(name, N, du):
+def test_early_polish_same_optimum_fewer_iterations(name, N, du, check):
     g = load_golden("optima.npz")
     lit = controller(N, du, passes=5).solve_batch(g[f"{name}_x0"], g[f"{name}_ref"], u_prev=g[f"{name}_up"])
-    ear = controller(N, du, passes=5, early_polish=True).solve_batch(g[f"{name}_x0"], g[f"{name}_ref"], u_prev=g[f"{name}_up"])
+    ear = controller(N, du, passes=5, early_polish=True, check_termination=check).solve_batch(g[f"{name}_x0"], g[f"{name}_ref"], u_prev=g[f"{name}_up"])
     assert (ear.status == 1).all() and (ear.info[:, 2] > 0).all()
     assert np.abs(ear.u0 - g[f"{name}_u0"]).max() < 1e-8 and np.abs(ear.Xp - g[f"{name}_X"]).max() < 1e-6
     assert np.abs(ear.u0 - lit.u0).max() < 1e-9
