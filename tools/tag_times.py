@@ -18,7 +18,8 @@ N, B = int(sys.argv[1]), int(sys.argv[2]); early = bool(int(sys.argv[3])) if len
 par = MPCConfig(horizon=N).to_parameters(0.8)
 if N == 50: par = dataclasses.replace(par, du_bounds=((-12., 12.), (-0.02, 0.02)))
 x0, ref, up = make_batch(B, N, seed=3 if N == 50 else 2)
-ctl = MPCController(par, SolverSettings(eps_abs=1e-6, eps_rel=1e-6, polish_passes=5, polish_retry=2, early_polish=early), max_batch=B)
+ctl = MPCController(par, SolverSettings(eps_abs=1e-6, eps_rel=1e-6, polish_passes=5, polish_retry=2, early_polish=early,
+                                         check_termination=int(os.environ.get('CHECK', '25'))), max_batch=B)
 lib = L.load()
 d = lambda a: torch.as_tensor(a).cuda()
 dx0, dref, dup = d(x0), d(ref), d(up)
