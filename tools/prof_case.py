@@ -10,7 +10,8 @@ par = MPCConfig(horizon=N).to_parameters(0.8)
 if N == 50:
     par = dataclasses.replace(par, du_bounds=((-12., 12.), (-0.02, 0.02)))
 x0, ref, up = make_batch(B, N, seed=3 if N == 50 else 2)
-ctl = MPCController(par, SolverSettings(eps_abs=eps, eps_rel=eps, polish_passes=5, polish_retry=2, keep_iterate=bool(int(os.environ.get('KEEP','0'))), early_polish=bool(int(os.environ.get('EARLY','1')))), max_batch=B)
+ctl = MPCController(par, SolverSettings(eps_abs=eps, eps_rel=eps, polish_passes=5, polish_retry=2, keep_iterate=bool(int(os.environ.get('KEEP','0'))), early_polish=bool(int(os.environ.get('EARLY','1'))),
+                                         check_termination=int(os.environ.get('CHECK', '25'))), max_batch=B)
 d = lambda a: torch.as_tensor(a).cuda()
 dx0, dref, dup = d(x0), d(ref), d(up)
 for _ in range(2):
