@@ -13,7 +13,7 @@ if N == 50: par = dataclasses.replace(par, du_bounds=((-12., 12.), (-0.02, 0.02)
 x0, ref, up = make_batch(B, N, seed=3 if N == 50 else 2)
 kw = dict(eps_abs=eps, eps_rel=eps, polish_passes=5, polish_retry=2, early_polish=bool(int(os.environ.get('EARLY','1'))))
 for k, v in os.environ.items():     # SET_<FIELD>=value overrides a SolverSettings field
-    if k.startswith("SET_"): kw[k[4:].lower()] = type(getattr(SolverSettings(), k[4:].lower()))(float(v))
+    if k.startswith("SET_"): kw[k[4:].lower()] = int(v) if k == "SET_EARLY_POLISH" else type(getattr(SolverSettings(), k[4:].lower()))(float(v))
 ctl = MPCController(par, SolverSettings(**kw), max_batch=B)
 d = lambda a: torch.as_tensor(a).cuda()
 dx0, dref, dup = d(x0), d(ref), d(up)
