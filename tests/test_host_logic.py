@@ -30,6 +30,11 @@ def test_params_to_c_roundtrip():
     assert c.q[0] == 4.0 and c.q[5] == 4.0 and c.q[10] == 0.6 and c.q[15] == 0.1 and c.q[1] == 0.0
     s = SolverSettings(eps_abs=1e-6, eps_rel=1e-6, polish=False).to_c()
     assert s.polish_passes == 0 and s.eps_abs == 1e-6 and s.max_iter == 60000
+    d = SolverSettings().to_c()                       # the reference's call: OSQP defaults for everything it does not pass
+    assert (d.check_termination, d.adaptive_rho_interval, d.early_polish, d.polish_retry, d.warm_start) == (25, 50, 0, 0, 0)
+    e = SolverSettings.early_certified().to_c()       # what bench.py's headline runs
+    assert (e.eps_abs, e.polish_passes, e.polish_retry, e.early_polish, e.check_termination, e.warm_start) == (1e-6, 5, 4, 1, 50, -1)
+    assert SolverSettings.early_certified(1e-4, polish_retry=2).to_c().polish_retry == 2
 
 
 def test_synthetic_batches_are_deterministic_and_shardable():
